@@ -1,0 +1,375 @@
+#!/usr/bin/env python3
+"""bench.py -- FNO rollout steps/sec on 64x64 cavity fields (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--batch B] [--act bf16|f32]
+
+One "step" = one `generate()` of the whole per-GPU batch (one autoregressive rollout step,
+SURVEY.md 8d).  N=1 workload = BASELINE.json configs[1]: cavity (p=5), batch 256, hidden activations
+stored as bf16, fp32 arithmetic; the fp32-storage (parity) mode is measured in the same run and reported
+under "fp32_storage".  N>1 (torchrun, one rank per GPU): each rank rolls out its own 256 cases, no
+data-path collective ("weak" scaling); value = N*K / max-over-ranks time.
+
+The printed JSON line carries, besides the contract keys: "e2e" (public API, HOST buffers, H2D+D2H inside
+the timed region every step), "roofline" (dominant kernel, algorithmic bytes / CUDA-event duration /
+measured HBM peak), "kernels" (per-kernel mean durations from a second, event-bracketed pass),
+"cpu_baseline" (oracle torch port = the reference's own library calls, timed on this host's cores),
+"rel_l2" (per-step relative L2 vs the fp32 CPU oracle on identical inputs) and "clocks".
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+from cfdbench_b200 import dp, synth  # noqa: E402
+
+METRIC = "fno_rollout_steps_per_sec"
+UNIT = "steps/s"
+HW = 64 * 64
+
+
+def measured_hbm_peak():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(path) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    except Exception:  # noqa: BLE001
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except Exception:  # noqa: BLE001
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self) -> dict:
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:  # noqa: BLE001
+            self.proc.kill()
+        sm, mx, pw, reasons = [], [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            parts = [p.strip() for p in ln.split(",")]
+            if len(parts) < 7:
+                continue
+            try:
+                sm.append(float(parts[0])); mx.append(float(parts[1])); pw.append(float(parts[2]))
+            except ValueError:
+                continue
+            for n, v in zip(names, parts[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def build_model(act: str, p: int, seed: int = 0):
+    from cfdbench_b200 import Fno2d, loss_name_to_fn
+    sd = synth.make_state_dict(seed, n_params=p)
+    m = Fno2d(in_chan=2, out_chan=2, n_case_params=p, loss_fn=loss_name_to_fn("nmse"), num_layers=synth.DEPTH,
+              hidden_dim=synth.HIDDEN, modes1=synth.MODES, modes2=synth.MODES,
+              act_dtype="bfloat16" if act == "bf16" else "float32")
+    m.load_state_dict({k: torch.from_numpy(v) for k, v in sd.items()})
+    return m, sd
+
+
+def timed_rollout(model, inp, cp, mk, steps: int, warmup: int):
+    """K steps = one native rollout of K steps on torch's current stream, CUDA events around it."""
+    dev = model.device
+    for _ in range(max(warmup, 0)):
+        model.generate_many(inp, cp, mk, 1)
+    torch.cuda.synchronize(dev)
+    if torch.distributed.is_initialized():
+        torch.distributed.barrier()
+    torch.cuda.synchronize(dev)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    seq = model.generate_many(inp, cp, mk, steps)
+    e1.record()
+    torch.cuda.synchronize(dev)
+    if torch.distributed.is_initialized():
+        torch.distributed.barrier()
+    torch.cuda.synchronize(dev)
+    return e0.elapsed_time(e1) / 1e3, seq
+
+
+def timed_e2e(model, batch: dict, steps: int, warmup: int):
+    """Public API with HOST buffers: every step copies that step's input frame (+mask, params) H2D from pinned
+    memory, runs generate(), and reads the predicted frame back D2H (fno_rollout_host with steps=1)."""
+    pin = {k: torch.from_numpy(batch[k]).pin_memory() for k in ("inputs", "case_params", "mask")}
+    cur = pin["inputs"]
+    for _ in range(max(warmup, 1)):
+        model.generate_many(cur, pin["case_params"], pin["mask"], 1)
+    torch.cuda.synchronize(model.device)
+    t0 = time.perf_counter()
+    cur = pin["inputs"]
+    for _ in range(steps):
+        cur = model.generate_many(cur, pin["case_params"], pin["mask"], 1)[0]  # syncs: result is on the host
+    t = time.perf_counter() - t0
+    b = batch["inputs"].shape[0]
+    h2d = b * (2 + 1) * HW * 4 + batch["case_params"].nbytes
+    d2h = b * 2 * HW * 4
+    return t, h2d, d2h
+
+
+def kernel_pass(model, inp, cp, mk, steps: int):
+    """Second pass with CUDA events around every kernel launch (same stream): mean duration per kernel."""
+    from cfdbench_b200 import _lib
+    lib = _lib.load()
+    b = inp.shape[0]
+    pk = model._pack()
+    ws, bufs = model._workspace(b)
+    w = pk["struct"]
+    act = model._act_code()
+    st = model._stream()
+    acts = [bufs["act0"], bufs["act1"]]
+    preds = torch.empty(b, 2, 64, 64, device=model.device)
+    names = ["lift", "dft_fwd", "mode_mix", "block_out", "project"]
+    evs = {n: [] for n in names}
+
+    def timed(name, fn):
+        a, z = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        _lib.check(fn(), name)
+        z.record()
+        evs[name].append((a, z))
+
+    cur_in = inp
+    inv = 1.0 / HW
+    for _ in range(steps):
+        timed("lift", lambda: lib.fno_lift_fwd(cur_in.data_ptr(), mk.data_ptr(), cp.data_ptr(), C.byref(w),
+                                               acts[0].data_ptr(), b, act, st))
+        cur = 0
+        for l in range(model.num_layers):
+            timed("dft_fwd", lambda: lib.fno_spectral_dft_fwd(acts[cur].data_ptr(), bufs["xm"].data_ptr(), b, act, 1.0, 1.0, st))
+            timed("mode_mix", lambda: lib.fno_mode_mix(bufs["xm"].data_ptr(), w.spec_wk[l], bufs["ym"].data_ptr(), b, st))
+            timed("block_out", lambda: lib.fno_block_out(_lib.EPI_GELU, bufs["ym"].data_ptr(), acts[cur].data_ptr(),
+                                                         w.w0t[l], w.w0_b[l], acts[cur ^ 1].data_ptr(), None, None, b,
+                                                         act, inv, 2 * inv, st))
+            cur ^= 1
+        timed("project", lambda: lib.fno_project_fwd(acts[cur].data_ptr(), mk.data_ptr(), C.byref(w), preds.data_ptr(), b, act, st))
+        cur_in = preds
+    torch.cuda.synchronize(model.device)
+    out = {}
+    for n in names:
+        ms = [a.elapsed_time(z) for a, z in evs[n]]
+        out[n] = {"mean_us": 1e3 * float(np.mean(ms)), "launches_per_step": len(ms) // steps}
+    return out
+
+
+def rel_l2_vs_oracle(model, sd, batch, steps: int = 4, nsamp: int = 2):
+    """Per-step relative L2 vs the fp32 CPU oracle (torch port == reference library calls) on identical
+    inputs (teacher-forced: both get the oracle's previous frame)."""
+    from oracle import fno_numpy as onp
+    from oracle import fno_torch_port as opt
+    pp = opt.params_from_numpy(sd)
+    inp = torch.from_numpy(batch["inputs"][:nsamp])
+    cp = torch.from_numpy(batch["case_params"][:nsamp])
+    mk = torch.from_numpy(batch["mask"][:nsamp])
+    out, cur = [], inp
+    with torch.no_grad():
+        for _ in range(steps):
+            ref = opt.forward(pp, cur, cp, mk)["preds"]
+            got = model.generate(cur.cuda(), cp.cuda(), mk.cuda()).cpu()
+            out.append(onp.rel_l2(got.numpy(), ref.numpy().astype(np.float64)))
+            cur = ref
+    return out
+
+
+def cpu_baseline(sd, batch, budget_s: float = 20.0, max_steps: int = 8):
+    """The reference's CPU path (oracle port: same torch.fft / einsum / conv2d / gelu calls) on this host."""
+    from oracle import fno_torch_port as opt
+    pp = opt.params_from_numpy(sd)
+    inp, cp, mk = (torch.from_numpy(batch[k]) for k in ("inputs", "case_params", "mask"))
+    with torch.no_grad():
+        opt.forward(pp, inp, cp, mk)  # warm-up
+        ts, cur, t_start = [], inp, time.perf_counter()
+        while len(ts) < max_steps and (time.perf_counter() - t_start) < budget_s:
+            t0 = time.perf_counter()
+            cur = opt.forward(pp, cur, cp, mk)["preds"]
+            ts.append(time.perf_counter() - t0)
+    med = float(np.median(ts))
+    return {"value": 1.0 / med, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
+            "sample": f"{len(ts)} rollout steps of the same B={inp.shape[0]} cavity batch, fp32, "
+                      f"torch {torch.__version__} CPU, median {med * 1e3:.1f} ms/step"}
+
+
+def run_reference(args, rank: int, world: int):
+    """--impl reference: the reference's own CPU implementation of the path (oracle port; /root/reference does
+    not exist on the GPU box and the reference is pure Python/PyTorch, so there is nothing to compile)."""
+    if rank != 0:
+        return
+    torch.set_num_threads(os.cpu_count() or 1)
+    from oracle import fno_torch_port as opt
+    p = synth.n_case_params("cavity")
+    sd = synth.make_state_dict(0, n_params=p)
+    batch = synth.make_batch(1, args.batch, "cavity", with_label=False)
+    pp = opt.params_from_numpy(sd)
+    inp, cp, mk = (torch.from_numpy(batch[k]) for k in ("inputs", "case_params", "mask"))
+    cur = inp
+    with torch.no_grad():
+        for _ in range(args.warmup):
+            cur = opt.forward(pp, cur, cp, mk)["preds"]
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            cur = opt.forward(pp, cur, cp, mk)["preds"]
+        t = time.perf_counter() - t0
+    val = args.steps / t
+    line = {
+        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * t / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"FNO autoregressive rollout, cavity (p=5), batch {args.batch}, 64x64x2, CPU fp32",
+                   "batch_per_step": args.batch},
+        "sample_steps_per_s": val * args.batch,
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
+                         "sample": f"{args.steps} rollout steps, B={args.batch}, torch {torch.__version__} CPU"},
+        "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=256, help="cases per GPU")
+    ap.add_argument("--act", default="bf16", choices=["bf16", "f32"], help="headline activation storage")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--graph", action="store_true", help="replay the rollout from a CUDA graph")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (the product path has no CPU fallback)")
+    rank, local, world = dp.init_from_env("nccl")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    p = synth.n_case_params("cavity")
+    batch = synth.make_batch(1 + rank, args.batch, "cavity", with_label=False)  # seed 0(+rank) shards
+    inp, cp, mk = (torch.from_numpy(batch[k]).to(dev) for k in ("inputs", "case_params", "mask"))
+
+    results = {}
+    sampler = ClockSampler(local)
+    for act in ([args.act] + [a for a in ("bf16", "f32") if a != args.act]):
+        model, sd = build_model(act, p)
+        model.graph_rollout = args.graph
+        headline = act == args.act
+        if headline and rank == 0:
+            sampler.start()
+        t, _ = timed_rollout(model, inp, cp, mk, args.steps, args.warmup)
+        if headline and rank == 0:
+            clocks = sampler.stop()
+        t_max = dp.max_over_ranks(t, dev)
+        r = {"t": t_max}
+        if rank == 0:
+            r["kernels"] = kernel_pass(model, inp, cp, mk, min(args.steps, 5))
+            r["rel_l2"] = rel_l2_vs_oracle(model, sd, batch)
+        if headline:
+            te, h2d, d2h = timed_e2e(model, batch, args.steps, 1)
+            r["e2e"] = (dp.max_over_ranks(te, dev), h2d, d2h)
+        results[act] = r
+        del model
+        torch.cuda.empty_cache()
+
+    if rank != 0:
+        if torch.distributed.is_initialized():
+            torch.distributed.destroy_process_group()
+        return
+
+    peak, peak_src = measured_hbm_peak()
+
+    def summarize(act):
+        r = results[act]
+        elt = 2 if act == "bf16" else 4
+        k3 = r["kernels"]["block_out"]["mean_us"] * 1e-6
+        alg = args.batch * 32 * HW * 2 * elt  # 32*64*64*(s_in+s_out) per sample-layer x samples/launch
+        blk = sum(r["kernels"][n]["mean_us"] for n in ("dft_fwd", "mode_mix", "block_out")) * 1e-6
+        step_us = sum(v["mean_us"] * v["launches_per_step"] for v in r["kernels"].values())
+        return {
+            "value": world * args.steps / r["t"], "ms_per_step": 1e3 * r["t"] / args.steps,
+            "roofline": {"bound": "hbm", "kernel": "block_out_kernel", "achieved": alg / k3 / 1e9, "peak": peak,
+                         "unit": "GB/s", "frac": alg / k3 / 1e9 / peak, "traffic": None,
+                         "algorithmic_bytes_per_launch": alg, "peak_source": peak_src,
+                         "share_of_step": r["kernels"]["block_out"]["mean_us"] * 4 / step_us,
+                         "fourier_layer_frac": alg / blk / 1e9 / peak},
+            "kernels": r["kernels"], "rel_l2": r["rel_l2"],
+        }
+
+    head = summarize(args.act)
+    other_act = "f32" if args.act == "bf16" else "bf16"
+    other = summarize(other_act)
+    te, h2d, d2h = results[args.act]["e2e"]
+    line = {
+        "metric": METRIC, "value": head["value"], "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": head["ms_per_step"], "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {
+            "workload": f"FNO autoregressive rollout, cavity_prop_bc_geo shape (p=5), batch {args.batch}/GPU, 64x64x2 "
+                        f"fields, 4 Fourier layers x 32 ch x 12x12 modes (BASELINE.json configs[1])",
+            "batch_per_gpu": args.batch, "global_batch": args.batch * world,
+            "act_storage": "bf16" if args.act == "bf16" else "f32", "arithmetic": "fp32",
+            "parallelism": f"dp{world} (independent case shards, no data-path collective)",
+            "l2": "inputs larger than L2: per-step working set (2 activation buffers + modes) = "
+                  f"{(2 * args.batch * 32 * HW * (2 if args.act == 'bf16' else 4) + 2 * args.batch * 288 * 32 * 8) / 1e6:.0f} MB > 126 MB",
+            "cuda_graph": bool(args.graph),
+        },
+        "sample_steps_per_s": head["value"] * args.batch,
+        "e2e": {"value": world * args.steps / te, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+        "gpu_launches": args.steps * (2 + 3 * synth.DEPTH),
+        "roofline": head["roofline"], "kernels": head["kernels"], "rel_l2": head["rel_l2"],
+        ("fp32_storage" if other_act == "f32" else "bf16_storage"): other,
+        "clocks": clocks,
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        line["cpu_baseline"] = cpu_baseline(synth.make_state_dict(0, n_params=p), batch)
+    print(json.dumps(line))
+    if torch.distributed.is_initialized():
+        torch.distributed.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,281 @@
+// extern "C" surface of libcfdbench_b200.so (declared in include/cfdbench_b200.h).
+#include <stdio.h>
+#include <string.h>
+
+#include "../../include/cfdbench_b200.h"
+#include "fno_common.cuh"
+
+namespace fno {
+template <typename TAct>
+cudaError_t launch_dft_fwd(const void*, void*, int, float, float, cudaStream_t);
+cudaError_t launch_mode_mix(const void*, const void*, void*, int, cudaStream_t);
+cudaError_t launch_pack_spectral(const void*, const void*, void*, int, cudaStream_t);
+cudaError_t launch_unpack_spectral(const void*, void*, void*, cudaStream_t);
+template <typename TAct>
+cudaError_t launch_block_out(int, const void*, const void*, const float*, const float*, void*, float*, const float*,
+                             int, float, float, cudaStream_t);
+template <typename TAct>
+cudaError_t launch_lift(const float*, const float*, const float*, const float*, const float*, const float*,
+                        const float*, void*, int, int, cudaStream_t);
+template <typename TAct>
+cudaError_t launch_project(const void*, const float*, const float*, const float*, const float*, const float*, float*,
+                           int, cudaStream_t);
+template <typename TAct>
+cudaError_t launch_project_bwd(const void*, const float*, const float*, const float*, const float*, const float*,
+                               const float*, float*, float*, float*, float*, float*, int, cudaStream_t);
+template <typename TP, typename TQ, int NJ, int NI>
+cudaError_t launch_chan_outer(const void*, const void*, float*, float*, int, cudaStream_t);
+cudaError_t launch_spectral_wgrad(const void*, const void*, void*, int, cudaStream_t);
+cudaError_t launch_lift_bwd(const float*, const float*, const float*, const float*, const float*, const float*,
+                            float*, float*, int, int, cudaStream_t);
+}  // namespace fno
+
+using namespace fno;
+
+static thread_local char g_err[512] = "";
+
+static int fail(int code, const char* what, cudaError_t e = cudaSuccess) {
+  if (e != cudaSuccess)
+    snprintf(g_err, sizeof(g_err), "%s: %s (%s)", what, cudaGetErrorName(e), cudaGetErrorString(e));
+  else
+    snprintf(g_err, sizeof(g_err), "%s", what);
+  return code;
+}
+#define FNO_CUDA(call, what)                         \
+  do {                                               \
+    cudaError_t _e = (call);                         \
+    if (_e != cudaSuccess) return fail(kErrCuda, what, _e); \
+  } while (0)
+#define FNO_TRY(call)        \
+  do {                       \
+    int _r = (call);         \
+    if (_r != kOk) return _r; \
+  } while (0)
+
+static inline cudaStream_t S(void* s) { return static_cast<cudaStream_t>(s); }
+static inline bool bad_dtype(int d) { return d != FNO_ACT_F32 && d != FNO_ACT_BF16; }
+
+extern "C" {
+
+int fno_version(void) { return FNO_ABI_VERSION; }
+const char* fno_last_error(void) { return g_err; }
+
+size_t fno_act_bytes(int batch, int act_dtype) {
+  return static_cast<size_t>(batch) * kC * kHW * (act_dtype == FNO_ACT_BF16 ? 2 : 4);
+}
+size_t fno_modes_bytes(int batch) { return static_cast<size_t>(batch) * kModes * kC * sizeof(float2); }
+
+int fno_pack_spectral_weights(const void* w1, const void* w2, void* wk, int conj_transpose, void* stream) {
+  if (!w1 || !w2 || !wk) return fail(kErrArg, "fno_pack_spectral_weights: null pointer");
+  FNO_CUDA(launch_pack_spectral(w1, w2, wk, conj_transpose, S(stream)), "pack_spectral_kernel");
+  return kOk;
+}
+
+int fno_unpack_spectral_grads(const void* gwk, void* gw1, void* gw2, void* stream) {
+  if (!gwk || !gw1 || !gw2) return fail(kErrArg, "fno_unpack_spectral_grads: null pointer");
+  FNO_CUDA(launch_unpack_spectral(gwk, gw1, gw2, S(stream)), "unpack_spectral_kernel");
+  return kOk;
+}
+
+int fno_lift_fwd(const float* inputs, const float* mask, const float* case_params, const fno_weights* w,
+                 void* act_out, int batch, int act_dtype, void* stream) {
+  if (!inputs || !mask || !w || !act_out || batch <= 0 || bad_dtype(act_dtype))
+    return fail(kErrArg, "fno_lift_fwd: bad argument");
+  if (w->n_case_params > 0 && !case_params) return fail(kErrArg, "fno_lift_fwd: case_params is null");
+  cudaError_t e = act_dtype == FNO_ACT_F32
+                      ? launch_lift<float>(inputs, mask, case_params, w->fc0_w, w->fc0_b, w->gx, w->gy, act_out, batch,
+                                           w->n_case_params, S(stream))
+                      : launch_lift<__nv_bfloat16>(inputs, mask, case_params, w->fc0_w, w->fc0_b, w->gx, w->gy,
+                                                   act_out, batch, w->n_case_params, S(stream));
+  FNO_CUDA(e, "lift_kernel");
+  return kOk;
+}
+
+int fno_spectral_dft_fwd(const void* act_in, void* xm, int batch, int act_dtype, float s0, float s1, void* stream) {
+  if (!act_in || !xm || batch <= 0 || bad_dtype(act_dtype)) return fail(kErrArg, "fno_spectral_dft_fwd: bad argument");
+  cudaError_t e = act_dtype == FNO_ACT_F32 ? launch_dft_fwd<float>(act_in, xm, batch, s0, s1, S(stream))
+                                           : launch_dft_fwd<__nv_bfloat16>(act_in, xm, batch, s0, s1, S(stream));
+  FNO_CUDA(e, "dft_fwd_kernel");
+  return kOk;
+}
+
+int fno_mode_mix(const void* xm, const void* wk, void* ym, int batch, void* stream) {
+  if (!xm || !wk || !ym || batch <= 0) return fail(kErrArg, "fno_mode_mix: bad argument");
+  FNO_CUDA(launch_mode_mix(xm, wk, ym, batch, S(stream)), "mode_mix_kernel");
+  return kOk;
+}
+
+int fno_block_out(int epilogue, const void* ym, const void* act_in, const float* w0t, const float* bias,
+                  void* act_out, float* pre_out, const float* pre_in, int batch, int act_dtype, float s0, float s1,
+                  void* stream) {
+  if (!ym || !act_in || !w0t || !act_out || batch <= 0 || bad_dtype(act_dtype))
+    return fail(kErrArg, "fno_block_out: bad argument");
+  if (epilogue == FNO_EPI_GELU_SAVE_PRE && !pre_out) return fail(kErrArg, "fno_block_out: pre_out is null");
+  if (epilogue == FNO_EPI_MUL_DGELU && !pre_in) return fail(kErrArg, "fno_block_out: pre_in is null");
+  cudaError_t e = act_dtype == FNO_ACT_F32
+                      ? launch_block_out<float>(epilogue, ym, act_in, w0t, bias, act_out, pre_out, pre_in, batch, s0,
+                                                s1, S(stream))
+                      : launch_block_out<__nv_bfloat16>(epilogue, ym, act_in, w0t, bias, act_out, pre_out, pre_in,
+                                                        batch, s0, s1, S(stream));
+  FNO_CUDA(e, "block_out_kernel");
+  return kOk;
+}
+
+int fno_block_fwd(const fno_weights* w, int layer, const void* act_in, void* act_out, float* pre_out,
+                  const fno_workspace* ws, int batch, int act_dtype, void* stream) {
+  if (!w || !ws || layer < 0 || layer >= w->n_layers) return fail(kErrArg, "fno_block_fwd: bad argument");
+  FNO_TRY(fno_spectral_dft_fwd(act_in, ws->xm, batch, act_dtype, 1.f, 1.f, stream));
+  FNO_TRY(fno_mode_mix(ws->xm, w->spec_wk[layer], ws->ym, batch, stream));
+  const float inv = 1.f / static_cast<float>(kHW);
+  return fno_block_out(pre_out ? FNO_EPI_GELU_SAVE_PRE : FNO_EPI_GELU, ws->ym, act_in, w->w0t[layer], w->w0_b[layer],
+                       act_out, pre_out, nullptr, batch, act_dtype, inv, 2.f * inv, stream);
+}
+
+int fno_project_fwd(const void* act_in, const float* mask, const fno_weights* w, float* preds, int batch,
+                    int act_dtype, void* stream) {
+  if (!act_in || !mask || !w || !preds || batch <= 0 || bad_dtype(act_dtype))
+    return fail(kErrArg, "fno_project_fwd: bad argument");
+  cudaError_t e = act_dtype == FNO_ACT_F32
+                      ? launch_project<float>(act_in, w->fc1_w, w->fc1_b, w->fc2_w, w->fc2_b, mask, preds, batch, S(stream))
+                      : launch_project<__nv_bfloat16>(act_in, w->fc1_w, w->fc1_b, w->fc2_w, w->fc2_b, mask, preds,
+                                                      batch, S(stream));
+  FNO_CUDA(e, "project_kernel");
+  return kOk;
+}
+
+int fno_forward(const fno_weights* w, const float* inputs, const float* mask, const float* case_params,
+                float* preds, const fno_workspace* ws, int batch, int act_dtype, void* stream) {
+  if (!w || !ws || !ws->act[0] || !ws->act[1] || !ws->xm || !ws->ym) return fail(kErrArg, "fno_forward: bad workspace");
+  if (w->n_layers < 1 || w->n_layers > FNO_MAX_LAYERS) return fail(kErrUnsupported, "fno_forward: n_layers out of range");
+  FNO_TRY(fno_lift_fwd(inputs, mask, case_params, w, ws->act[0], batch, act_dtype, stream));
+  int cur = 0;
+  for (int l = 0; l < w->n_layers; ++l) {
+    FNO_TRY(fno_block_fwd(w, l, ws->act[cur], ws->act[cur ^ 1], nullptr, ws, batch, act_dtype, stream));
+    cur ^= 1;
+  }
+  return fno_project_fwd(ws->act[cur], mask, w, preds, batch, act_dtype, stream);
+}
+
+int fno_rollout(const fno_weights* w, const float* inputs, const float* mask, const float* case_params,
+                float* preds_seq, int steps, const fno_workspace* ws, int batch, int act_dtype, void* stream) {
+  if (steps < 0 || !preds_seq) return fail(kErrArg, "fno_rollout: bad argument");
+  const size_t frame = static_cast<size_t>(batch) * 2 * kHW;
+  const float* cur = inputs;
+  for (int s = 0; s < steps; ++s) {
+    float* nxt = preds_seq + static_cast<size_t>(s) * frame;
+    FNO_TRY(fno_forward(w, cur, mask, case_params, nxt, ws, batch, act_dtype, stream));
+    cur = nxt;
+  }
+  return kOk;
+}
+
+size_t fno_rollout_host_scratch_bytes(int batch, int n_case_params, int steps) {
+  const size_t b = static_cast<size_t>(batch);
+  return (b * 2 * kHW + b * kHW + static_cast<size_t>(steps) * b * 2 * kHW) * sizeof(float) +
+         ((b * n_case_params * sizeof(float) + 255) / 256) * 256;
+}
+
+int fno_rollout_host(const fno_weights* w, const float* inputs_host, const float* mask_host,
+                     const float* case_params_host, float* preds_seq_host, int steps, const fno_workspace* ws,
+                     void* dev_io, int batch, int act_dtype, void* stream) {
+  if (!w || !inputs_host || !mask_host || !preds_seq_host || !dev_io || batch <= 0 || steps <= 0)
+    return fail(kErrArg, "fno_rollout_host: bad argument");
+  const size_t b = static_cast<size_t>(batch);
+  float* d_in = static_cast<float*>(dev_io);
+  float* d_mask = d_in + b * 2 * kHW;
+  float* d_seq = d_mask + b * kHW;
+  float* d_params = d_seq + static_cast<size_t>(steps) * b * 2 * kHW;
+  cudaStream_t st = S(stream);
+  FNO_CUDA(cudaMemcpyAsync(d_in, inputs_host, b * 2 * kHW * sizeof(float), cudaMemcpyHostToDevice, st), "H2D inputs");
+  FNO_CUDA(cudaMemcpyAsync(d_mask, mask_host, b * kHW * sizeof(float), cudaMemcpyHostToDevice, st), "H2D mask");
+  if (w->n_case_params > 0)
+    FNO_CUDA(cudaMemcpyAsync(d_params, case_params_host, b * w->n_case_params * sizeof(float), cudaMemcpyHostToDevice, st),
+             "H2D case_params");
+  FNO_TRY(fno_rollout(w, d_in, d_mask, d_params, d_seq, steps, ws, batch, act_dtype, stream));
+  FNO_CUDA(cudaMemcpyAsync(preds_seq_host, d_seq, static_cast<size_t>(steps) * b * 2 * kHW * sizeof(float),
+                           cudaMemcpyDeviceToHost, st),
+           "D2H preds");
+  return kOk;
+}
+
+int fno_forward_train(const fno_weights* w, const float* inputs, const float* mask, const float* case_params,
+                      float* preds, const fno_train_saved* saved, const fno_workspace* ws, int batch,
+                      int act_dtype, void* stream) {
+  if (!w || !saved || !ws || !ws->ym) return fail(kErrArg, "fno_forward_train: bad argument");
+  if (w->n_layers < 1 || w->n_layers > FNO_MAX_LAYERS) return fail(kErrUnsupported, "fno_forward_train: n_layers");
+  FNO_TRY(fno_lift_fwd(inputs, mask, case_params, w, saved->act[0], batch, act_dtype, stream));
+  const float inv = 1.f / static_cast<float>(kHW);
+  for (int l = 0; l < w->n_layers; ++l) {
+    if (!saved->act[l + 1] || !saved->pre[l] || !saved->xm[l]) return fail(kErrArg, "fno_forward_train: null saved buffer");
+    FNO_TRY(fno_spectral_dft_fwd(saved->act[l], saved->xm[l], batch, act_dtype, 1.f, 1.f, stream));
+    FNO_TRY(fno_mode_mix(saved->xm[l], w->spec_wk[l], ws->ym, batch, stream));
+    FNO_TRY(fno_block_out(FNO_EPI_GELU_SAVE_PRE, ws->ym, saved->act[l], w->w0t[l], w->w0_b[l], saved->act[l + 1],
+                          saved->pre[l], nullptr, batch, act_dtype, inv, 2.f * inv, stream));
+  }
+  return fno_project_fwd(saved->act[w->n_layers], mask, w, preds, batch, act_dtype, stream);
+}
+
+int fno_backward(const fno_weights* w, const fno_weights_bwd* wb, const float* inputs, const float* mask,
+                 const float* case_params, const float* dpreds, const fno_train_saved* saved,
+                 const fno_grads* g, const fno_bwd_scratch* sc, const fno_workspace* ws, int batch,
+                 int act_dtype, void* stream) {
+  if (!w || !wb || !inputs || !mask || !dpreds || !saved || !g || !sc || !ws || batch <= 0 || bad_dtype(act_dtype))
+    return fail(kErrArg, "fno_backward: bad argument");
+  if (!sc->d[0] || !sc->d[1] || !sc->dz1 || !sc->gm || !sc->gwk || !ws->ym)
+    return fail(kErrArg, "fno_backward: null scratch buffer");
+  cudaStream_t st = S(stream);
+  const int L = w->n_layers, p = w->n_case_params;
+  const bool bf = act_dtype == FNO_ACT_BF16;
+  // small gradients are accumulated with atomics: clear them first
+  FNO_CUDA(cudaMemsetAsync(g->fc0_w, 0, sizeof(float) * kC * (5 + p), st), "memset");
+  FNO_CUDA(cudaMemsetAsync(g->fc0_b, 0, sizeof(float) * kC, st), "memset");
+  FNO_CUDA(cudaMemsetAsync(g->fc1_w, 0, sizeof(float) * kProj * kC, st), "memset");
+  FNO_CUDA(cudaMemsetAsync(g->fc1_b, 0, sizeof(float) * kProj, st), "memset");
+  FNO_CUDA(cudaMemsetAsync(g->fc2_w, 0, sizeof(float) * 2 * kProj, st), "memset");
+  FNO_CUDA(cudaMemsetAsync(g->fc2_b, 0, sizeof(float) * 2, st), "memset");
+  for (int l = 0; l < L; ++l) {
+    FNO_CUDA(cudaMemsetAsync(g->w0_w[l], 0, sizeof(float) * kC * kC, st), "memset");
+    FNO_CUDA(cudaMemsetAsync(g->w0_b[l], 0, sizeof(float) * kC, st), "memset");
+  }
+  // ---- project backward (batch chunks bound the dz1 scratch) -> d[0] = dpre_{L-1}
+  const size_t act_elt = bf ? 2 : 4;
+  for (int b0 = 0; b0 < batch; b0 += FNO_BWD_CHUNK) {
+    const int nb = (batch - b0 < FNO_BWD_CHUNK) ? batch - b0 : FNO_BWD_CHUNK;
+    const char* a_l = static_cast<const char*>(saved->act[L]) + static_cast<size_t>(b0) * kC * kHW * act_elt;
+    const float* pre = saved->pre[L - 1] + static_cast<size_t>(b0) * kC * kHW;
+    float* dout = sc->d[0] + static_cast<size_t>(b0) * kC * kHW;
+    const float* dp = dpreds + static_cast<size_t>(b0) * 2 * kHW;
+    const float* mk = mask + static_cast<size_t>(b0) * kHW;
+    cudaError_t e =
+        bf ? launch_project_bwd<__nv_bfloat16>(a_l, dp, mk, pre, w->fc1_w, w->fc1_b, w->fc2_w, dout, sc->dz1, g->fc2_w,
+                                               g->fc2_b, g->fc1_b, nb, st)
+           : launch_project_bwd<float>(a_l, dp, mk, pre, w->fc1_w, w->fc1_b, w->fc2_w, dout, sc->dz1, g->fc2_w,
+                                       g->fc2_b, g->fc1_b, nb, st);
+    FNO_CUDA(e, "project_bwd_kernel");
+    e = bf ? launch_chan_outer<float, __nv_bfloat16, 128, 32>(sc->dz1, a_l, g->fc1_w, nullptr, nb, st)
+           : launch_chan_outer<float, float, 128, 32>(sc->dz1, a_l, g->fc1_w, nullptr, nb, st);
+    FNO_CUDA(e, "chan_outer_kernel(fc1)");
+  }
+  // ---- Fourier blocks, last to first
+  const float inv = 1.f / static_cast<float>(kHW);
+  int cur = 0;
+  for (int l = L - 1; l >= 0; --l) {
+    float* dpre = sc->d[cur];
+    float* dnext = sc->d[cur ^ 1];
+    cudaError_t e = bf ? launch_chan_outer<float, __nv_bfloat16, 32, 32>(dpre, saved->act[l], g->w0_w[l], g->w0_b[l], batch, st)
+                       : launch_chan_outer<float, float, 32, 32>(dpre, saved->act[l], g->w0_w[l], g->w0_b[l], batch, st);
+    FNO_CUDA(e, "chan_outer_kernel(w0)");
+    FNO_TRY(fno_spectral_dft_fwd(dpre, sc->gm, batch, FNO_ACT_F32, inv, 2.f * inv, stream));
+    FNO_CUDA(launch_spectral_wgrad(saved->xm[l], sc->gm, sc->gwk, batch, st), "spectral_wgrad_kernel");
+    FNO_TRY(fno_unpack_spectral_grads(sc->gwk, g->spec_w1[l], g->spec_w2[l], stream));
+    FNO_TRY(fno_mode_mix(sc->gm, wb->spec_wkT[l], ws->ym, batch, stream));
+    FNO_TRY(fno_block_out(l > 0 ? FNO_EPI_MUL_DGELU : FNO_EPI_PLAIN, ws->ym, dpre, wb->w0[l], nullptr, dnext, nullptr,
+                          l > 0 ? saved->pre[l - 1] : nullptr, batch, FNO_ACT_F32, 1.f, 1.f, stream));
+    cur ^= 1;
+  }
+  FNO_CUDA(launch_lift_bwd(sc->d[cur], inputs, mask, case_params, w->gx, w->gy, g->fc0_w, g->fc0_b, batch, p, st),
+           "lift_bwd_kernel");
+  return kOk;
+}
+
+}  // extern "C"

@@ -1,0 +1,418 @@
+// Backward-only kernels of the FNO training step (what torch.autograd derives for the reference's
+// Fno2d.forward when train_auto.py:255 calls loss["nmse"].backward()).  The data-gradient path of a
+// Fourier block reuses the forward kernels (K1 with the c_ky/4096 output scale, K2 with the
+// conj-transposed weight pack, K3 with W0 un-transposed and the MUL_DGELU / PLAIN epilogues); this
+// file holds what is new in the backward direction:
+//   project_bwd_kernel   d(fc1,GELU,fc2,mask): recomputes the 128-wide hidden layer per pixel, emits
+//                        dpre of the last block (or d a_L), dz1 for the fc1 weight gradient, and the
+//                        fc2 / bias gradients
+//   chan_outer_kernel    G[j][i] += sum_{b,pix} P[b][j][pix] Q[b][i][pix]  (1x1-conv weight gradients)
+//   spectral_wgrad_kernel  gWk[k][i][o] = sum_b conj(X[b][k][i]) G[b][k][o]   
+//   lift_bwd_kernel      gradients of fc0 (spatial feature columns + folded per-sample constants)
+#include "fno_common.cuh"
+
+namespace fno {
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// GELU and its derivative sharing one erfc evaluation
+__device__ __forceinline__ void gelu_both(float x, float& g, float& dg) {
+  const float ax = fabsf(x);
+  const float e = 0.5f * erfc_abs_scaled(ax);  // 0.5 erfc(|x|/sqrt2)
+  g = fmaxf(x, 0.f) - ax * e;
+  const float cdf = x >= 0.f ? 1.f - e : e;
+  const float pdf = 0.3989422804014327f * exp2f(-0.7213475204444817f * x * x);
+  dg = fmaf(x, pdf, cdf);
+}
+
+// ------------------------------------------------------------------------------------ project bwd
+constexpr int kPbThreads = 128;
+constexpr int kPbPix = 256;
+
+template <typename TAct>
+struct PbSmem {
+  alignas(128) TAct xs[kC][kPbPix];
+  alignas(16) float w1[kProj][kC];
+  alignas(16) float b1[kProj];
+  alignas(16) float w2[2][kProj];
+  alignas(16) float acc_w2[2][kProj];
+  alignas(16) float acc_b1[kProj];
+  alignas(8) uint64_t bar;
+};
+
+template <typename TAct>
+__global__ void __launch_bounds__(kPbThreads)
+    project_bwd_kernel(const TAct* __restrict__ a,        // [B][32][4096]  a_L
+                       const float* __restrict__ dpreds,  // [B][2][4096]
+                       const float* __restrict__ mask,    // [B][4096]
+                       const float* __restrict__ pre,     // [B][32][4096] pre-activation of the last block (or null)
+                       const float* __restrict__ w1, const float* __restrict__ b1, const float* __restrict__ w2,
+                       float* __restrict__ d_out,         // [B][32][4096]: dpre_{L-1} (pre != null) or d a_L
+                       float* __restrict__ dz1,           // [B][128][4096]
+                       float* __restrict__ g_w2, float* __restrict__ g_b2, float* __restrict__ g_b1) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  PbSmem<TAct>& sm = *reinterpret_cast<PbSmem<TAct>*>(smem_raw);
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int b = blockIdx.y;
+  const int pix0 = blockIdx.x * kPbPix;
+
+  if (tid == 0) {
+    mbar_init(&sm.bar, 1);
+    fence_mbar_init();
+  }
+  __syncthreads();
+  if (tid < kC) {
+    constexpr uint32_t bytes = kPbPix * sizeof(TAct);
+    if (tid == 0) mbar_expect_tx(&sm.bar, kC * bytes);
+    __syncwarp();
+    bulk_g2s(&sm.xs[tid][0], a + (static_cast<size_t>(b) * kC + tid) * kHW + pix0, bytes, &sm.bar);
+  }
+  for (int i = tid; i < kProj * kC; i += kPbThreads) (&sm.w1[0][0])[i] = w1[i];
+  for (int j = tid; j < kProj; j += kPbThreads) {
+    sm.b1[j] = b1[j];
+    sm.w2[0][j] = w2[j];
+    sm.w2[1][j] = w2[kProj + j];
+    sm.acc_w2[0][j] = 0.f;
+    sm.acc_w2[1][j] = 0.f;
+    sm.acc_b1[j] = 0.f;
+  }
+  __syncthreads();
+  mbar_wait(&sm.bar, 0);
+
+  const int pix = pix0 + 2 * tid;
+  float2 x[kC], da[kC];
+#pragma unroll
+  for (int i = 0; i < kC; ++i) {
+    if constexpr (sizeof(TAct) == 4) {
+      x[i] = *reinterpret_cast<const float2*>(&sm.xs[i][2 * tid]);
+    } else {
+      const uint32_t v = *reinterpret_cast<const uint32_t*>(&sm.xs[i][2 * tid]);
+      x[i] = make_float2(__uint_as_float(v << 16), __uint_as_float(v & 0xffff0000u));
+    }
+    da[i] = make_float2(0.f, 0.f);
+  }
+  const float2 m = *reinterpret_cast<const float2*>(mask + static_cast<size_t>(b) * kHW + pix);
+  float2 d0 = *reinterpret_cast<const float2*>(dpreds + (static_cast<size_t>(b) * 2 + 0) * kHW + pix);
+  float2 d1 = *reinterpret_cast<const float2*>(dpreds + (static_cast<size_t>(b) * 2 + 1) * kHW + pix);
+  d0.x *= m.x; d0.y *= m.y; d1.x *= m.x; d1.y *= m.y;
+
+  float* dz_b = dz1 + static_cast<size_t>(b) * kProj * kHW + pix;
+#pragma unroll 1
+  for (int j = 0; j < kProj; ++j) {
+    float wr[kC];
+    const float4* wrow = reinterpret_cast<const float4*>(&sm.w1[j][0]);
+#pragma unroll
+    for (int q = 0; q < kC / 4; ++q) {
+      const float4 t = wrow[q];
+      wr[4 * q] = t.x; wr[4 * q + 1] = t.y; wr[4 * q + 2] = t.z; wr[4 * q + 3] = t.w;
+    }
+    const float bj = sm.b1[j];
+    float2 z0 = make_float2(bj, bj), z1 = make_float2(0.f, 0.f);
+#pragma unroll
+    for (int i = 0; i < kC; i += 2) {
+      z0 = __ffma2_rn(x[i], make_float2(wr[i], wr[i]), z0);
+      z1 = __ffma2_rn(x[i + 1], make_float2(wr[i + 1], wr[i + 1]), z1);
+    }
+    const float2 z = make_float2(z0.x + z1.x, z0.y + z1.y);
+    float gx_, gy_, dgx, dgy;
+    gelu_both(z.x, gx_, dgx);
+    gelu_both(z.y, gy_, dgy);
+    const float w20 = sm.w2[0][j], w21 = sm.w2[1][j];
+    const float2 dz = make_float2((w20 * d0.x + w21 * d1.x) * dgx, (w20 * d0.y + w21 * d1.y) * dgy);
+#pragma unroll
+    for (int i = 0; i < kC; ++i) da[i] = __ffma2_rn(make_float2(wr[i], wr[i]), dz, da[i]);
+    *reinterpret_cast<float2*>(dz_b + static_cast<size_t>(j) * kHW) = dz;
+    // fc2 weight gradient and fc1 bias gradient: warp partials -> smem accumulators
+    const float p0 = warp_sum(d0.x * gx_ + d0.y * gy_);
+    const float p1 = warp_sum(d1.x * gx_ + d1.y * gy_);
+    const float pb = warp_sum(dz.x + dz.y);
+    if (lane == 0) {
+      atomicAdd(&sm.acc_w2[0][j], p0);
+      atomicAdd(&sm.acc_w2[1][j], p1);
+      atomicAdd(&sm.acc_b1[j], pb);
+    }
+  }
+  // fc2 bias gradient
+  {
+    const float s0 = warp_sum(d0.x + d0.y), s1 = warp_sum(d1.x + d1.y);
+    if (lane == 0) {
+      atomicAdd(g_b2 + 0, s0);
+      atomicAdd(g_b2 + 1, s1);
+    }
+  }
+  // d a_L (optionally times GELU'(pre_{L-1}))
+  const size_t base = static_cast<size_t>(b) * kC * kHW + pix;
+#pragma unroll
+  for (int i = 0; i < kC; ++i) {
+    float2 v = da[i];
+    if (pre != nullptr) {
+      const float2 pv = *reinterpret_cast<const float2*>(pre + base + static_cast<size_t>(i) * kHW);
+      v.x *= dgelu_erf(pv.x);
+      v.y *= dgelu_erf(pv.y);
+    }
+    *reinterpret_cast<float2*>(d_out + base + static_cast<size_t>(i) * kHW) = v;
+  }
+  __syncthreads();
+  for (int j = tid; j < kProj; j += kPbThreads) {
+    atomicAdd(g_w2 + j, sm.acc_w2[0][j]);
+    atomicAdd(g_w2 + kProj + j, sm.acc_w2[1][j]);
+    atomicAdd(g_b1 + j, sm.acc_b1[j]);
+  }
+}
+
+template <typename TAct>
+cudaError_t launch_project_bwd(const void* a, const float* dpreds, const float* mask, const float* pre,
+                               const float* w1, const float* b1, const float* w2, float* d_out, float* dz1,
+                               float* g_w2, float* g_b2, float* g_b1, int batch, cudaStream_t stream) {
+  auto kern = project_bwd_kernel<TAct>;
+  constexpr size_t smem = sizeof(PbSmem<TAct>);
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    configured = true;
+  }
+  dim3 grid(kHW / kPbPix, batch);
+  kern<<<grid, kPbThreads, smem, stream>>>(static_cast<const TAct*>(a), dpreds, mask, pre, w1, b1, w2, d_out, dz1,
+                                           g_w2, g_b2, g_b1);
+  return cudaGetLastError();
+}
+template cudaError_t launch_project_bwd<float>(const void*, const float*, const float*, const float*, const float*,
+                                               const float*, const float*, float*, float*, float*, float*, float*,
+                                               int, cudaStream_t);
+template cudaError_t launch_project_bwd<__nv_bfloat16>(const void*, const float*, const float*, const float*,
+                                                       const float*, const float*, const float*, float*, float*,
+                                                       float*, float*, float*, int, cudaStream_t);
+
+// ------------------------------------------------------------------------------------- chan outer
+// out[j][i] += sum_{b,pix} P[b][j][pix] * Q[b][i][pix];   rowsum[j] += sum_{b,pix} P[b][j][pix]
+constexpr int kCoThreads = 256;
+constexpr int kCoPix = 128;
+constexpr int kCoPitch = kCoPix + 4;
+
+template <typename T>
+__device__ __forceinline__ float4 load4(const T* p);
+template <>
+__device__ __forceinline__ float4 load4<float>(const float* p) {
+  return *reinterpret_cast<const float4*>(p);
+}
+template <>
+__device__ __forceinline__ float4 load4<__nv_bfloat16>(const __nv_bfloat16* p) {
+  const uint2 v = *reinterpret_cast<const uint2*>(p);
+  return make_float4(__uint_as_float(v.x << 16), __uint_as_float(v.x & 0xffff0000u), __uint_as_float(v.y << 16),
+                     __uint_as_float(v.y & 0xffff0000u));
+}
+
+template <typename TP, typename TQ, int NJ, int NI>
+__global__ void __launch_bounds__(kCoThreads)
+    chan_outer_kernel(const TP* __restrict__ P, const TQ* __restrict__ Q, float* __restrict__ out,
+                      float* __restrict__ rowsum, int batch) {
+  constexpr int TJ = (NJ * NI / kCoThreads >= 16) ? 4 : 2;
+  constexpr int TI = NJ * NI / kCoThreads / TJ;
+  constexpr int NTI = NI / TI;
+  static_assert(TJ * TI * kCoThreads == NJ * NI, "tile mismatch");
+  extern __shared__ __align__(16) float smem_f[];
+  float* ps = smem_f;                    // [NJ][pitch]
+  float* qs = smem_f + NJ * kCoPitch;    // [NI][pitch]
+  const int tid = threadIdx.x;
+  const int tj = tid / NTI, ti = tid % NTI;
+  float acc[TJ][TI];
+  float rs[TJ];
+#pragma unroll
+  for (int a = 0; a < TJ; ++a) {
+    rs[a] = 0.f;
+#pragma unroll
+    for (int c = 0; c < TI; ++c) acc[a][c] = 0.f;
+  }
+  const int chunks = kHW / kCoPix;
+  const int items = batch * chunks;
+  for (int it = blockIdx.x; it < items; it += gridDim.x) {
+    const int b = it / chunks, p0 = (it % chunks) * kCoPix;
+    __syncthreads();
+    for (int e = tid; e < NJ * (kCoPix / 4); e += kCoThreads) {
+      const int j = e / (kCoPix / 4), q = e % (kCoPix / 4);
+      *reinterpret_cast<float4*>(ps + j * kCoPitch + 4 * q) =
+          load4<TP>(P + (static_cast<size_t>(b) * NJ + j) * kHW + p0 + 4 * q);
+    }
+    for (int e = tid; e < NI * (kCoPix / 4); e += kCoThreads) {
+      const int i = e / (kCoPix / 4), q = e % (kCoPix / 4);
+      *reinterpret_cast<float4*>(qs + i * kCoPitch + 4 * q) =
+          load4<TQ>(Q + (static_cast<size_t>(b) * NI + i) * kHW + p0 + 4 * q);
+    }
+    __syncthreads();
+#pragma unroll 4
+    for (int q = 0; q < kCoPix / 4; ++q) {
+      float4 pv[TJ], qv[TI];
+#pragma unroll
+      for (int a = 0; a < TJ; ++a) pv[a] = *reinterpret_cast<const float4*>(ps + (tj * TJ + a) * kCoPitch + 4 * q);
+#pragma unroll
+      for (int c = 0; c < TI; ++c) qv[c] = *reinterpret_cast<const float4*>(qs + (ti * TI + c) * kCoPitch + 4 * q);
+#pragma unroll
+      for (int a = 0; a < TJ; ++a) {
+        rs[a] += (pv[a].x + pv[a].y) + (pv[a].z + pv[a].w);
+#pragma unroll
+        for (int c = 0; c < TI; ++c)
+          acc[a][c] = fmaf(pv[a].x, qv[c].x, fmaf(pv[a].y, qv[c].y, fmaf(pv[a].z, qv[c].z, fmaf(pv[a].w, qv[c].w, acc[a][c]))));
+      }
+    }
+  }
+#pragma unroll
+  for (int a = 0; a < TJ; ++a) {
+#pragma unroll
+    for (int c = 0; c < TI; ++c) atomicAdd(out + (tj * TJ + a) * NI + ti * TI + c, acc[a][c]);
+    if (rowsum != nullptr && ti == 0) atomicAdd(rowsum + tj * TJ + a, rs[a]);
+  }
+}
+
+template <typename TP, typename TQ, int NJ, int NI>
+cudaError_t launch_chan_outer(const void* P, const void* Q, float* out, float* rowsum, int batch, cudaStream_t stream) {
+  auto kern = chan_outer_kernel<TP, TQ, NJ, NI>;
+  constexpr size_t smem = static_cast<size_t>(NJ + NI) * kCoPitch * sizeof(float);
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    configured = true;
+  }
+  const int items = batch * (kHW / kCoPix);
+  const int grid = items < 296 ? items : 296;
+  kern<<<grid, kCoThreads, smem, stream>>>(static_cast<const TP*>(P), static_cast<const TQ*>(Q), out, rowsum, batch);
+  return cudaGetLastError();
+}
+template cudaError_t launch_chan_outer<float, float, 128, 32>(const void*, const void*, float*, float*, int, cudaStream_t);
+template cudaError_t launch_chan_outer<float, __nv_bfloat16, 128, 32>(const void*, const void*, float*, float*, int, cudaStream_t);
+template cudaError_t launch_chan_outer<float, float, 32, 32>(const void*, const void*, float*, float*, int, cudaStream_t);
+template cudaError_t launch_chan_outer<float, __nv_bfloat16, 32, 32>(const void*, const void*, float*, float*, int, cudaStream_t);
+
+// --------------------------------------------------------------------------------- spectral wgrad
+// gWk[k][i][o] = sum_b conj(X[b][k][i]) * G[b][k][o];  one CTA per mode k, lane = o, warps split the batch.
+constexpr int kSwWarps = 4;
+
+__global__ void __launch_bounds__(kSwWarps * 32)
+    spectral_wgrad_kernel(const float2* __restrict__ xm, const float2* __restrict__ gm, float2* __restrict__ gwk,
+                          int batch) {
+  __shared__ __align__(16) float2 xs[kSwWarps][kC];
+  __shared__ __align__(16) float2 red[kSwWarps][kC][kC + 1];
+  const int k = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float2 acc_a[kC], acc_b[kC];  // a += xr*(gr,gi); b += xi*(gr,gi);  conj(x)*g = (a.x + b.y, a.y - b.x)
+#pragma unroll
+  for (int i = 0; i < kC; ++i) acc_a[i] = acc_b[i] = make_float2(0.f, 0.f);
+  for (int b = warp; b < batch; b += kSwWarps) {
+    const size_t off = (static_cast<size_t>(b) * kModes + k) * kC + lane;
+    const float2 xv = __ldg(xm + off);
+    const float2 g = __ldg(gm + off);
+    __syncwarp();
+    xs[warp][lane] = xv;
+    __syncwarp();
+#pragma unroll
+    for (int i = 0; i < kC; i += 2) {
+      const float4 v = *reinterpret_cast<const float4*>(&xs[warp][i]);
+      acc_a[i] = __ffma2_rn(make_float2(v.x, v.x), g, acc_a[i]);
+      acc_b[i] = __ffma2_rn(make_float2(v.y, v.y), g, acc_b[i]);
+      acc_a[i + 1] = __ffma2_rn(make_float2(v.z, v.z), g, acc_a[i + 1]);
+      acc_b[i + 1] = __ffma2_rn(make_float2(v.w, v.w), g, acc_b[i + 1]);
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < kC; ++i) red[warp][i][lane] = make_float2(acc_a[i].x + acc_b[i].y, acc_a[i].y - acc_b[i].x);
+  __syncthreads();
+  for (int e = threadIdx.x; e < kC * kC; e += kSwWarps * 32) {
+    const int i = e / kC, o = e % kC;
+    float2 s = red[0][i][o];
+#pragma unroll
+    for (int w = 1; w < kSwWarps; ++w) {
+      s.x += red[w][i][o].x;
+      s.y += red[w][i][o].y;
+    }
+    gwk[static_cast<size_t>(k) * kC * kC + e] = s;
+  }
+}
+
+cudaError_t launch_spectral_wgrad(const void* xm, const void* gm, void* gwk, int batch, cudaStream_t stream) {
+  spectral_wgrad_kernel<<<kModes, kSwWarps * 32, 0, stream>>>(static_cast<const float2*>(xm), static_cast<const float2*>(gm),
+                                                             static_cast<float2*>(gwk), batch);
+  return cudaGetLastError();
+}
+
+// --------------------------------------------------------------------------------------- lift bwd
+// g_w[c][q] (q<5: u,v,mask,x,y; q>=5: case params), g_b[c] from d a0.  One CTA per (channel c, sample
+// slice); per-sample plane sums T[b][c] carry the bias and case-parameter columns.
+constexpr int kLbThreads = 256;
+
+__global__ void __launch_bounds__(kLbThreads)
+    lift_bwd_kernel(const float* __restrict__ da0,     // [B][32][4096]
+                    const float* __restrict__ inputs,  // [B][2][4096]
+                    const float* __restrict__ mask,    // [B][4096]
+                    const float* __restrict__ params,  // [B][p]
+                    const float* __restrict__ gx, const float* __restrict__ gy, float* __restrict__ g_w,
+                    float* __restrict__ g_b, int batch, int p) {
+  __shared__ float red[kLbThreads / 32][6];
+  __shared__ float tot[6];
+  const int c = blockIdx.x;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int nin = 5 + p;
+  float gw_acc[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
+  float gb_acc = 0.f;
+  float gp_acc[kMaxCaseParams];
+#pragma unroll
+  for (int q = 0; q < kMaxCaseParams; ++q) gp_acc[q] = 0.f;
+  for (int b = blockIdx.y; b < batch; b += gridDim.y) {
+    float s[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    const float* d = da0 + (static_cast<size_t>(b) * kC + c) * kHW;
+    for (int px = tid * 4; px < kHW; px += kLbThreads * 4) {
+      const float4 dv = *reinterpret_cast<const float4*>(d + px);
+      const float4 u = *reinterpret_cast<const float4*>(inputs + (static_cast<size_t>(b) * 2 + 0) * kHW + px);
+      const float4 v = *reinterpret_cast<const float4*>(inputs + (static_cast<size_t>(b) * 2 + 1) * kHW + px);
+      const float4 m = *reinterpret_cast<const float4*>(mask + static_cast<size_t>(b) * kHW + px);
+      const float4 yw = *reinterpret_cast<const float4*>(gy + (px & 63));
+      const float xh = gx[px >> 6];
+      const float dsum = (dv.x + dv.y) + (dv.z + dv.w);
+      s[0] += dv.x * u.x + dv.y * u.y + dv.z * u.z + dv.w * u.w;
+      s[1] += dv.x * v.x + dv.y * v.y + dv.z * v.z + dv.w * v.w;
+      s[2] += dv.x * m.x + dv.y * m.y + dv.z * m.z + dv.w * m.w;
+      s[3] += dsum * xh;
+      s[4] += dv.x * yw.x + dv.y * yw.y + dv.z * yw.z + dv.w * yw.w;
+      s[5] += dsum;
+    }
+#pragma unroll
+    for (int q = 0; q < 6; ++q) {
+      const float r = warp_sum(s[q]);
+      if (lane == 0) red[warp][q] = r;
+    }
+    __syncthreads();
+    if (tid < 6) {
+      float t = 0.f;
+      for (int w = 0; w < kLbThreads / 32; ++w) t += red[w][tid];
+      tot[tid] = t;
+    }
+    __syncthreads();
+    if (tid == 0) {
+#pragma unroll
+      for (int q = 0; q < 5; ++q) gw_acc[q] += tot[q];
+      gb_acc += tot[5];
+      for (int q = 0; q < p; ++q) gp_acc[q] += tot[5] * params[b * p + q];
+    }
+    __syncthreads();
+  }
+  if (tid == 0) {
+#pragma unroll
+    for (int q = 0; q < 5; ++q) atomicAdd(g_w + c * nin + q, gw_acc[q]);
+    for (int q = 0; q < p; ++q) atomicAdd(g_w + c * nin + 5 + q, gp_acc[q]);
+    atomicAdd(g_b + c, gb_acc);
+  }
+}
+
+cudaError_t launch_lift_bwd(const float* da0, const float* inputs, const float* mask, const float* params,
+                            const float* gx, const float* gy, float* g_w, float* g_b, int batch, int p,
+                            cudaStream_t stream) {
+  if (p < 0 || p > kMaxCaseParams) return cudaErrorInvalidValue;
+  dim3 grid(kC, batch < 16 ? batch : 16);
+  lift_bwd_kernel<<<grid, kLbThreads, 0, stream>>>(da0, inputs, mask, params, gx, gy, g_w, g_b, batch, p);
+  return cudaGetLastError();
+}
+
+}  // namespace fno

@@ -1,0 +1,146 @@
+// Shared definitions for the sm_100a FNO kernels (cfdbench_b200).
+//
+// Problem constants are the reference's FNO configuration (reference src/args.py:99-103,187-197:
+// 64x64 grid, fno_hidden_dim=32, fno_modes_x=fno_modes_y=12); the Python wrapper rejects anything
+// else, there is no generic / CPU fallback.
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace fno {
+
+constexpr int kH = 64;
+constexpr int kW = 64;
+constexpr int kHW = kH * kW;
+constexpr int kC = 32;        // hidden channels
+constexpr int kM1 = 12;       // kept |kx| modes per corner
+constexpr int kM2 = 12;       // kept ky modes
+constexpr int kKX = 2 * kM1;  // kept kx rows: 0..11 (weights1) and 52..63 (weights2)
+constexpr int kModes = kKX * kM2;  // 288 complex modes per (sample, channel)
+constexpr int kProj = 128;    // fc1 width (reference fno2d.py:175)
+constexpr int kMaxCaseParams = 16;
+
+// ------------------------------------------------------------------------------------------------
+// mbarrier + 1-D bulk-copy (TMA engine, SASS UBLKCP) wrappers.  A plane of an NCHW activation is a
+// contiguous 16 KB (fp32) / 8 KB (bf16) run, so plain bulk copies are enough: no tensor map needed.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void fence_mbar_init() {
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+          smem_u32(dst_smem)),
+      "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+      : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  while (!mbar_try_wait(bar, parity)) {
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Activation storage types.  Arithmetic is always fp32; TAct only selects how hidden activations
+// are stored in HBM between kernels (float = parity mode, bf16 = BASELINE.json's bf16 batches).
+// ------------------------------------------------------------------------------------------------
+template <typename T>
+struct Act;
+template <>
+struct Act<float> {
+  static __device__ __forceinline__ float ld(const float* p) { return *p; }
+  static __device__ __forceinline__ void st(float* p, float v) { *p = v; }
+};
+template <>
+struct Act<__nv_bfloat16> {
+  static __device__ __forceinline__ float ld(const __nv_bfloat16* p) { return __bfloat162float(*p); }
+  static __device__ __forceinline__ void st(__nv_bfloat16* p, float v) { *p = __float2bfloat16_rn(v); }
+};
+
+// ------------------------------------------------------------------------------------------------
+// Exact (erf) GELU, nn.GELU() default (reference fno2d.py:147), evaluated without erff():
+//   GELU(x) = max(x,0) - 0.5|x| * erfc(|x|/sqrt2),   erfc(z) = 2^{p(z)}, p = degree-8 minimax fit
+// |exp2(p)-erfc| <= 1.5e-8 on [0,4.5]; beyond 4.5 erfc < 2e-10 and z is clamped.  In fp32 the result
+// is within 2.7e-7 abs of the float64 GELU (torch's own fp32 GELU: 1.3e-6), see tests/test_gelu.py.
+// One MUFU.EX2 + 8 FFMA per element, branch-free, and vectorises to FFMA2 on float2.
+// ------------------------------------------------------------------------------------------------
+#define FNO_GELU_C0 2.1715042208825253e-08f
+#define FNO_GELU_C1 -1.6279093256885822f
+#define FNO_GELU_C2 -0.918409818247829f
+#define FNO_GELU_C3 -0.1485066268693784f
+#define FNO_GELU_C4 0.028301834411822168f
+#define FNO_GELU_C5 -0.0008250955854016083f
+#define FNO_GELU_C6 -0.001460431044966736f
+#define FNO_GELU_C7 0.0004369618322752869f
+#define FNO_GELU_C8 -4.4355305747040687e-05f
+
+__device__ __forceinline__ float erfc_abs_scaled(float ax) {  // erfc(ax/sqrt2), ax >= 0
+  const float z = fminf(ax * 0.70710678118654752f, 4.5f);
+  float p = FNO_GELU_C8;
+  p = fmaf(p, z, FNO_GELU_C7);
+  p = fmaf(p, z, FNO_GELU_C6);
+  p = fmaf(p, z, FNO_GELU_C5);
+  p = fmaf(p, z, FNO_GELU_C4);
+  p = fmaf(p, z, FNO_GELU_C3);
+  p = fmaf(p, z, FNO_GELU_C2);
+  p = fmaf(p, z, FNO_GELU_C1);
+  p = fmaf(p, z, FNO_GELU_C0);
+  return exp2f(p);
+}
+__device__ __forceinline__ float gelu_erf(float x) {
+  const float ax = fabsf(x);
+  return fmaxf(x, 0.f) - (0.5f * ax) * erfc_abs_scaled(ax);
+}
+// d/dx GELU(x) = Phi(x) + x phi(x)
+__device__ __forceinline__ float dgelu_erf(float x) {
+  const float ax = fabsf(x);
+  const float e = 0.5f * erfc_abs_scaled(ax);
+  const float cdf = x >= 0.f ? 1.f - e : e;
+  const float pdf = 0.3989422804014327f * exp2f(-0.7213475204444817f * x * x);
+  return fmaf(x, pdf, cdf);
+}
+
+// packed pair version (FFMA2 on sm_100)
+__device__ __forceinline__ float2 gelu_erf2(float2 x) {
+  const float2 ax = make_float2(fabsf(x.x), fabsf(x.y));
+  float2 z = make_float2(fminf(ax.x * 0.70710678118654752f, 4.5f), fminf(ax.y * 0.70710678118654752f, 4.5f));
+  float2 p = make_float2(FNO_GELU_C8, FNO_GELU_C8);
+  p = __ffma2_rn(p, z, make_float2(FNO_GELU_C7, FNO_GELU_C7));
+  p = __ffma2_rn(p, z, make_float2(FNO_GELU_C6, FNO_GELU_C6));
+  p = __ffma2_rn(p, z, make_float2(FNO_GELU_C5, FNO_GELU_C5));
+  p = __ffma2_rn(p, z, make_float2(FNO_GELU_C4, FNO_GELU_C4));
+  p = __ffma2_rn(p, z, make_float2(FNO_GELU_C3, FNO_GELU_C3));
+  p = __ffma2_rn(p, z, make_float2(FNO_GELU_C2, FNO_GELU_C2));
+  p = __ffma2_rn(p, z, make_float2(FNO_GELU_C1, FNO_GELU_C1));
+  p = __ffma2_rn(p, z, make_float2(FNO_GELU_C0, FNO_GELU_C0));
+  const float ex = exp2f(p.x), ey = exp2f(p.y);
+  return make_float2(fmaxf(x.x, 0.f) - (0.5f * ax.x) * ex, fmaxf(x.y, 0.f) - (0.5f * ax.y) * ey);
+}
+
+// status codes of the C ABI
+enum : int { kOk = 0, kErrArg = 1, kErrCuda = 2, kErrUnsupported = 3 };
+
+}  // namespace fno

@@ -1,0 +1,453 @@
+"""Drop-in `Fno2d` for CFDBench backed by the sm_100a kernels in libcfdbench_b200.so.
+
+Mirrors the reference module's public surface (reference src/models/fno/fno2d.py:115-295):
+same constructor keywords as `utils/autoregressive.py:114-125` passes, same parameter names /
+shapes / dtypes in `state_dict()` (fc0, blocks.{l}.conv0.weights1|weights2 (complex64),
+blocks.{l}.w0, fc1, fc2), same `forward / generate / generate_many` semantics, same return types.
+The sub-modules below are *parameter holders only*: all arithmetic happens in the CUDA library
+(`cfdbench_b200._lib`), there is no PyTorch/CPU fallback path.
+
+Extras that the reference does not have (all optional, defaults keep reference behaviour):
+  * `act_dtype="bfloat16"`: hidden activations are stored as bf16 between kernels (fp32 arithmetic).
+  * `generate_many(..)` runs the whole rollout in one native call; host tensors in -> host tensors out
+    through `fno_rollout_host` (H2D + rollout + D2H on one stream).
+  * `enable_data_parallel()`: all-reduce of one flat gradient buffer (NCCL) inside backward.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict, List, Optional
+
+import numpy as np
+import torch
+import torch.nn as nn
+from torch import Tensor
+
+from . import _lib
+from .base_model import AutoCfdModel
+
+H = W = 64
+HIDDEN = 32
+MODES = 12
+NMODES = 2 * MODES * MODES  # 288
+PROJ = 128
+
+
+class SpectralConv2d_fast(nn.Module):
+    """Parameter holder for the Fourier weights; init as reference fno2d.py:30-51
+    (scale * torch.rand(cfloat), scale = 1/(Cin*Cout))."""
+
+    def __init__(self, in_channels: int, out_channels: int, modes1: int, modes2: int, device=None):
+        super().__init__()
+        self.in_channels, self.out_channels = in_channels, out_channels
+        self.modes1, self.modes2 = modes1, modes2
+        self.scale = 1 / (in_channels * out_channels)
+        # generated on CPU then moved so that the RNG stream matches the reference's initialisation order
+        self.weights1 = nn.Parameter(
+            (self.scale * torch.rand(in_channels, out_channels, modes1, modes2, dtype=torch.cfloat)).to(device))
+        self.weights2 = nn.Parameter(
+            (self.scale * torch.rand(in_channels, out_channels, modes1, modes2, dtype=torch.cfloat)).to(device))
+
+    def forward(self, x):  # pragma: no cover
+        raise RuntimeError("SpectralConv2d_fast is a parameter holder; call Fno2d.forward")
+
+
+class FnoBlock(nn.Module):
+    """Parameter holder: conv0 (spectral weights) + w0 (1x1 conv), reference fno2d.py:85-104."""
+
+    def __init__(self, in_chan: int, out_chan: int, modes1: int, modes2: int, device=None):
+        super().__init__()
+        self.conv0 = SpectralConv2d_fast(in_chan, out_chan, modes1, modes2, device=device)
+        self.w0 = nn.Conv2d(in_chan, out_chan, 1).to(device)
+
+    def forward(self, x):  # pragma: no cover
+        raise RuntimeError("FnoBlock is a parameter holder; call Fno2d.forward")
+
+
+def _ptr(t: Optional[Tensor]) -> int:
+    return 0 if t is None else t.data_ptr()
+
+
+class _TrainFn(torch.autograd.Function):
+    """One autograd node for the whole network: forward = fno_forward_train, backward = fno_backward."""
+
+    @staticmethod
+    def forward(ctx, model: "Fno2d", inputs: Tensor, mask: Tensor, case_params: Tensor, *params: Tensor):
+        preds, saved = model._native_forward_train(inputs, mask, case_params)
+        ctx.model = model
+        ctx.saved_native = saved
+        ctx.save_for_backward(inputs, mask, case_params)
+        return preds
+
+    @staticmethod
+    def backward(ctx, dpreds: Tensor):
+        inputs, mask, case_params = ctx.saved_tensors
+        model: "Fno2d" = ctx.model
+        grads = model._native_backward(inputs, mask, case_params, dpreds.contiguous().float(), ctx.saved_native)
+        ctx.saved_native = None
+        return (None, None, None, None, *grads)
+
+
+class Fno2d(AutoCfdModel):
+    def __init__(
+        self,
+        in_chan: int,
+        out_chan: int,
+        n_case_params: int,
+        loss_fn: nn.Module,
+        num_layers: int,
+        modes1: int = 12,
+        modes2: int = 12,
+        hidden_dim: int = 20,
+        padding: Optional[int] = None,
+        act_dtype: str = "float32",
+        device=None,
+    ):
+        super().__init__(loss_fn)
+        if (hidden_dim, modes1, modes2) != (HIDDEN, MODES, MODES):
+            raise ValueError(
+                f"cfdbench_b200.Fno2d is specialised on hidden_dim=32, modes=12x12 (CFDBench's FNO config, "
+                f"reference src/args.py:187-197); got hidden_dim={hidden_dim}, modes=({modes1},{modes2})")
+        if in_chan != 2 or out_chan != 2:
+            raise ValueError("cfdbench_b200.Fno2d supports in_chan=out_chan=2 ((u,v) fields) only")
+        if padding is not None:
+            raise ValueError("padding is not supported (reference init_model never passes it)")
+        if not (1 <= num_layers <= _lib.FNO_MAX_LAYERS):
+            raise ValueError(f"num_layers must be in 1..{_lib.FNO_MAX_LAYERS}")
+        if not (0 <= n_case_params <= 16):
+            raise ValueError("n_case_params must be in 0..16")
+        if act_dtype not in ("float32", "bfloat16"):
+            raise ValueError("act_dtype must be 'float32' or 'bfloat16'")
+        self.in_chan, self.out_chan = in_chan, out_chan
+        self.n_case_params = n_case_params
+        self.num_layers = num_layers
+        self.modes1, self.modes2 = modes1, modes2
+        self.hidden_dim = hidden_dim
+        self.padding = padding
+        self.act_dtype = act_dtype
+        if device is None:
+            # no CPU path: parameters live on the current CUDA device when there is one (this also fixes the
+            # reference's missing .cuda() for fno, SURVEY.md 3.1 defect 2).  Without a GPU the module can still be
+            # built (state_dict round trips, CPU tests of the host logic) but forward raises.
+            device = torch.device("cuda", torch.cuda.current_device()) if torch.cuda.is_available() else torch.device("cpu")
+        device = torch.device(device)
+
+        # same construction order as the reference so that the RNG stream gives the same initial weights:
+        # fc0 -> per block (weights1, weights2, w0) -> fc1 -> fc2   (reference fno2d.py:150-176)
+        self.fc0 = nn.Conv2d(in_chan + 1 + 2 + n_case_params, hidden_dim, 1, 1, 0).to(device)
+        self.blocks = nn.Sequential(*[FnoBlock(hidden_dim, hidden_dim, modes1, modes2, device=device)
+                                      for _ in range(num_layers)])
+        self.fc1 = nn.Conv2d(hidden_dim, PROJ, 1, 1, 0).to(device)
+        self.fc2 = nn.Conv2d(PROJ, out_chan, 1, 1, 0).to(device)
+
+        self._pack_key = None
+        self._packed: dict = {}
+        self._ws_cache: dict = {}
+        self._dp_group = None
+        self._dp_enabled = False
+        self.graph_rollout = False
+        self._graphs: dict = {}
+
+    # ------------------------------------------------------------------------------------ plumbing
+    @property
+    def device(self) -> torch.device:
+        return self.fc0.weight.device
+
+    def _act_code(self) -> int:
+        return _lib.ACT_BF16 if self.act_dtype == "bfloat16" else _lib.ACT_F32
+
+    def _act_torch_dtype(self):
+        return torch.bfloat16 if self.act_dtype == "bfloat16" else torch.float32
+
+    def _require_cuda(self):
+        if self.device.type != "cuda":
+            raise _lib.FnoNativeError(
+                "cfdbench_b200.Fno2d has no CPU path: parameters are on %s; move the model to a CUDA device" % self.device)
+
+    def _stream(self) -> C.c_void_p:
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def _pack(self, need_bwd: bool = False) -> dict:
+        """(Re)build kernel-layout weights when any parameter changed (version counters / pointers)."""
+        plist = list(self.parameters())
+        key = tuple((p.data_ptr(), p._version) for p in plist)
+        pk = self._packed
+        if key != self._pack_key:
+            lib = _lib.load()
+            dev = self.device
+            for p in plist:
+                if not p.is_contiguous():
+                    raise _lib.FnoNativeError("parameters must be contiguous")
+            pk = {"wk": [], "w0t": [], "wkT": None}
+            st = self._stream()
+            for blk in self.blocks:
+                wk = torch.empty(NMODES, HIDDEN, HIDDEN, dtype=torch.complex64, device=dev)
+                _lib.check(lib.fno_pack_spectral_weights(blk.conv0.weights1.data_ptr(), blk.conv0.weights2.data_ptr(),
+                                                         wk.data_ptr(), 0, st), "fno_pack_spectral_weights")
+                pk["wk"].append(wk)
+                pk["w0t"].append(blk.w0.weight.detach().view(HIDDEN, HIDDEN).t().contiguous())
+            if "gx" not in self._packed:
+                lin = torch.tensor(np.linspace(0, 1, H), dtype=torch.float)  # as reference fno2d.py:250-252
+                pk["gx"] = lin.to(dev)
+                pk["gy"] = lin.clone().to(dev)
+            else:
+                pk["gx"], pk["gy"] = self._packed["gx"], self._packed["gy"]
+            w = _lib.FnoWeights()
+            w.n_layers, w.n_case_params = self.num_layers, self.n_case_params
+            w.fc0_w, w.fc0_b = self.fc0.weight.data_ptr(), self.fc0.bias.data_ptr()
+            for l, blk in enumerate(self.blocks):
+                w.spec_wk[l] = pk["wk"][l].data_ptr()
+                w.w0t[l] = pk["w0t"][l].data_ptr()
+                w.w0_b[l] = blk.w0.bias.data_ptr()
+            w.fc1_w, w.fc1_b = self.fc1.weight.data_ptr(), self.fc1.bias.data_ptr()
+            w.fc2_w, w.fc2_b = self.fc2.weight.data_ptr(), self.fc2.bias.data_ptr()
+            w.gx, w.gy = pk["gx"].data_ptr(), pk["gy"].data_ptr()
+            pk["struct"] = w
+            self._packed, self._pack_key = pk, key
+            self._graphs.clear()
+        if need_bwd and pk.get("wkT") is None:
+            lib = _lib.load()
+            st = self._stream()
+            pk["wkT"] = []
+            wb = _lib.FnoWeightsBwd()
+            for l, blk in enumerate(self.blocks):
+                wkT = torch.empty(NMODES, HIDDEN, HIDDEN, dtype=torch.complex64, device=self.device)
+                _lib.check(lib.fno_pack_spectral_weights(blk.conv0.weights1.data_ptr(), blk.conv0.weights2.data_ptr(),
+                                                         wkT.data_ptr(), 1, st), "fno_pack_spectral_weights(T)")
+                pk["wkT"].append(wkT)
+                wb.spec_wkT[l] = wkT.data_ptr()
+                wb.w0[l] = blk.w0.weight.data_ptr()
+            pk["struct_bwd"] = wb
+        return pk
+
+    def _workspace(self, batch: int):
+        key = (batch, self.act_dtype, self.device)
+        ws = self._ws_cache.get(key)
+        if ws is None:
+            dev = self.device
+            adt = self._act_torch_dtype()
+            bufs = dict(
+                act0=torch.empty(batch, HIDDEN, H, W, dtype=adt, device=dev),
+                act1=torch.empty(batch, HIDDEN, H, W, dtype=adt, device=dev),
+                xm=torch.empty(batch, NMODES, HIDDEN, dtype=torch.complex64, device=dev),
+                ym=torch.empty(batch, NMODES, HIDDEN, dtype=torch.complex64, device=dev),
+            )
+            st = _lib.FnoWorkspace()
+            st.act[0], st.act[1] = bufs["act0"].data_ptr(), bufs["act1"].data_ptr()
+            st.xm, st.ym = bufs["xm"].data_ptr(), bufs["ym"].data_ptr()
+            ws = (st, bufs)
+            if len(self._ws_cache) > 4:
+                self._ws_cache.clear()
+            self._ws_cache[key] = ws
+        return ws
+
+    def _prep_inputs(self, inputs: Tensor, case_params: Tensor, mask: Optional[Tensor]):
+        if inputs.dim() != 4 or inputs.shape[1] != self.in_chan or tuple(inputs.shape[-2:]) != (H, W):
+            raise ValueError(f"inputs must be (B,{self.in_chan},{H},{W}); got {tuple(inputs.shape)}")
+        b = inputs.shape[0]
+        dev = self.device
+        inputs = inputs.to(device=dev, dtype=torch.float32, non_blocking=True).contiguous()
+        if case_params.shape != (b, self.n_case_params):
+            raise ValueError(f"case_params must be ({b},{self.n_case_params}); got {tuple(case_params.shape)}")
+        case_params = case_params.to(device=dev, dtype=torch.float32, non_blocking=True).contiguous()
+        if mask is None:
+            mask4 = torch.ones((b, 1, H, W), device=dev)  # reference fno2d.py:197-199
+        else:
+            mask4 = mask.unsqueeze(1) if mask.dim() == 3 else mask
+            if tuple(mask4.shape) != (b, 1, H, W):
+                raise ValueError(f"mask must be (B,{H},{W}) or (B,1,{H},{W}); got {tuple(mask.shape)}")
+            mask4 = mask4.to(device=dev, dtype=torch.float32, non_blocking=True).contiguous()
+        return inputs, case_params, mask4
+
+    # ------------------------------------------------------------------------------ native calls
+    def _native_forward(self, inputs: Tensor, mask4: Tensor, case_params: Tensor) -> Tensor:
+        lib = _lib.load()
+        b = inputs.shape[0]
+        pk = self._pack()
+        ws, _ = self._workspace(b)
+        preds = torch.empty(b, self.out_chan, H, W, dtype=torch.float32, device=self.device)
+        _lib.check(lib.fno_forward(C.byref(pk["struct"]), inputs.data_ptr(), mask4.data_ptr(), case_params.data_ptr(),
+                                   preds.data_ptr(), C.byref(ws), b, self._act_code(), self._stream()), "fno_forward")
+        return preds
+
+    def _native_forward_train(self, inputs: Tensor, mask4: Tensor, case_params: Tensor):
+        lib = _lib.load()
+        b, L, dev = inputs.shape[0], self.num_layers, self.device
+        pk = self._pack(need_bwd=True)
+        ws, _ = self._workspace(b)
+        adt = self._act_torch_dtype()
+        acts = [torch.empty(b, HIDDEN, H, W, dtype=adt, device=dev) for _ in range(L + 1)]
+        pres = [torch.empty(b, HIDDEN, H, W, dtype=torch.float32, device=dev) for _ in range(L)]
+        xms = [torch.empty(b, NMODES, HIDDEN, dtype=torch.complex64, device=dev) for _ in range(L)]
+        sv = _lib.FnoTrainSaved()
+        for l in range(L + 1):
+            sv.act[l] = acts[l].data_ptr()
+        for l in range(L):
+            sv.pre[l], sv.xm[l] = pres[l].data_ptr(), xms[l].data_ptr()
+        preds = torch.empty(b, self.out_chan, H, W, dtype=torch.float32, device=dev)
+        _lib.check(lib.fno_forward_train(C.byref(pk["struct"]), inputs.data_ptr(), mask4.data_ptr(),
+                                         case_params.data_ptr(), preds.data_ptr(), C.byref(sv), C.byref(ws), b,
+                                         self._act_code(), self._stream()), "fno_forward_train")
+        return preds, (sv, acts, pres, xms)
+
+    def _grad_layout(self):
+        """(name, param, offset, n_real) for one flat float32 gradient buffer, parameter order."""
+        out, off = [], 0
+        for name, p in self.named_parameters():
+            n = p.numel() * (2 if p.is_complex() else 1)
+            out.append((name, p, off, n))
+            off += n
+        return out, off
+
+    def _native_backward(self, inputs, mask4, case_params, dpreds, saved_native):
+        lib = _lib.load()
+        sv, acts, pres, xms = saved_native
+        b, L, dev = inputs.shape[0], self.num_layers, self.device
+        pk = self._pack(need_bwd=True)
+        ws, _ = self._workspace(b)
+        layout, total = self._grad_layout()
+        flat = torch.empty(total, dtype=torch.float32, device=dev)
+        views: Dict[str, Tensor] = {}
+        for name, p, off, n in layout:
+            seg = flat[off:off + n]
+            views[name] = torch.view_as_complex(seg.view(*p.shape, 2)) if p.is_complex() else seg.view(p.shape)
+        g = _lib.FnoGrads()
+        g.fc0_w, g.fc0_b = views["fc0.weight"].data_ptr(), views["fc0.bias"].data_ptr()
+        for l in range(L):
+            g.spec_w1[l] = views[f"blocks.{l}.conv0.weights1"].data_ptr()
+            g.spec_w2[l] = views[f"blocks.{l}.conv0.weights2"].data_ptr()
+            g.w0_w[l] = views[f"blocks.{l}.w0.weight"].data_ptr()
+            g.w0_b[l] = views[f"blocks.{l}.w0.bias"].data_ptr()
+        g.fc1_w, g.fc1_b = views["fc1.weight"].data_ptr(), views["fc1.bias"].data_ptr()
+        g.fc2_w, g.fc2_b = views["fc2.weight"].data_ptr(), views["fc2.bias"].data_ptr()
+        d0 = torch.empty(b, HIDDEN, H, W, dtype=torch.float32, device=dev)
+        d1 = torch.empty(b, HIDDEN, H, W, dtype=torch.float32, device=dev)
+        dz1 = torch.empty(min(b, _lib.BWD_CHUNK), PROJ, H, W, dtype=torch.float32, device=dev)
+        gm = torch.empty(b, NMODES, HIDDEN, dtype=torch.complex64, device=dev)
+        gwk = torch.empty(NMODES, HIDDEN, HIDDEN, dtype=torch.complex64, device=dev)
+        sc = _lib.FnoBwdScratch()
+        sc.d[0], sc.d[1] = d0.data_ptr(), d1.data_ptr()
+        sc.dz1, sc.gm, sc.gwk = dz1.data_ptr(), gm.data_ptr(), gwk.data_ptr()
+        _lib.check(lib.fno_backward(C.byref(pk["struct"]), C.byref(pk["struct_bwd"]), inputs.data_ptr(),
+                                    mask4.data_ptr(), case_params.data_ptr(), dpreds.data_ptr(), C.byref(sv),
+                                    C.byref(g), C.byref(sc), C.byref(ws), b, self._act_code(), self._stream()),
+                   "fno_backward")
+        if self._dp_enabled:
+            from .dp import allreduce_mean_
+            allreduce_mean_(flat, self._dp_group)
+        return [views[name] for name, _ in self.named_parameters()]
+
+    # -------------------------------------------------------------------------------- public API
+    def enable_data_parallel(self, group=None) -> None:
+        """Average gradients over `group` with one all-reduce of the flat gradient buffer at the end of
+        backward (the reference has no distributed code; train_auto.py builds no DDP wrapper, so the hook
+        lives in the module).  Replicas must start from identical weights."""
+        import torch.distributed as dist
+        if not dist.is_initialized():
+            raise RuntimeError("torch.distributed is not initialised")
+        self._dp_group, self._dp_enabled = group, True
+
+    def forward(self, inputs: Tensor, case_params: Tensor, mask: Optional[Tensor] = None,
+                label: Optional[Tensor] = None) -> Dict:
+        """Same contract as reference fno2d.py:178-242: returns {"preds": (B,2,H,W) float32 masked}
+        plus {"loss": dict} when `label` is given."""
+        self._require_cuda()
+        inputs, case_params, mask4 = self._prep_inputs(inputs, case_params, mask)
+        needs_grad = torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters())
+        with torch.cuda.device(self.device):
+            if needs_grad:
+                preds = _TrainFn.apply(self, inputs, mask4, case_params, *self.parameters())
+            else:
+                preds = self._native_forward(inputs, mask4, case_params)
+        if label is not None:
+            label = label.to(device=self.device, dtype=torch.float32) * mask4
+            return dict(preds=preds, loss=self.loss_fn(preds=preds, labels=label))
+        return dict(preds=preds)
+
+    def generate(self, inputs: Tensor, case_params: Tensor, mask: Optional[Tensor] = None) -> Tensor:
+        return self.forward(inputs=inputs, case_params=case_params, mask=mask)["preds"]
+
+    def generate_many(self, inputs: Tensor, case_params: Tensor, mask: Tensor, steps: int) -> List[Tensor]:
+        """reference fno2d.py:269-295.  Returns a list of `steps` tensors (B,c,h,w); tensors live where
+        `inputs` lives (host tensors take the H2D -> rollout -> D2H path in one native call)."""
+        self._require_cuda()
+        assert len(inputs.shape) == len(case_params.shape) + 2
+        if inputs.dim() == 3:
+            inputs, case_params, mask = inputs.unsqueeze(0), case_params.unsqueeze(0), mask.unsqueeze(0)
+        assert inputs.shape[0] == case_params.shape[0] == mask.shape[0]
+        if steps <= 0:
+            return []
+        host = inputs.device.type == "cpu"
+        with torch.no_grad(), torch.cuda.device(self.device):
+            if host:
+                seq = self._rollout_host(inputs, case_params, mask, steps)
+            else:
+                inputs, case_params, mask4 = self._prep_inputs(inputs, case_params, mask)
+                seq = self._rollout_device(inputs, case_params, mask4, steps)
+        return [seq[s] for s in range(steps)]
+
+    def _rollout_device(self, inputs, case_params, mask4, steps) -> Tensor:
+        lib = _lib.load()
+        b = inputs.shape[0]
+        pk = self._pack()
+        ws, _ = self._workspace(b)
+        seq = torch.empty(steps, b, self.out_chan, H, W, dtype=torch.float32, device=self.device)
+        if not self.graph_rollout:
+            _lib.check(lib.fno_rollout(C.byref(pk["struct"]), inputs.data_ptr(), mask4.data_ptr(),
+                                       case_params.data_ptr(), seq.data_ptr(), steps, C.byref(ws), b,
+                                       self._act_code(), self._stream()), "fno_rollout")
+            return seq
+        # CUDA-graph replay: static buffers, one capture per (batch, steps)
+        key = (b, steps, self.act_dtype)
+        ent = self._graphs.get(key)
+        if ent is None:
+            s_in, s_cp, s_mk = inputs.clone(), case_params.clone(), mask4.clone()
+            s_seq = torch.empty_like(seq)
+
+            def run():
+                _lib.check(lib.fno_rollout(C.byref(pk["struct"]), s_in.data_ptr(), s_mk.data_ptr(), s_cp.data_ptr(),
+                                           s_seq.data_ptr(), steps, C.byref(ws), b, self._act_code(),
+                                           self._stream()), "fno_rollout")
+            side = torch.cuda.Stream(device=self.device)
+            side.wait_stream(torch.cuda.current_stream(self.device))
+            with torch.cuda.stream(side):
+                run()  # warm-up: sets kernel attributes outside capture
+            torch.cuda.current_stream(self.device).wait_stream(side)
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                run()
+            ent = (graph, s_in, s_cp, s_mk, s_seq)
+            self._graphs[key] = ent
+        graph, s_in, s_cp, s_mk, s_seq = ent
+        s_in.copy_(inputs)
+        s_cp.copy_(case_params)
+        s_mk.copy_(mask4)
+        graph.replay()
+        seq.copy_(s_seq)
+        return seq
+
+    def _rollout_host(self, inputs: Tensor, case_params: Tensor, mask: Tensor, steps: int) -> Tensor:
+        lib = _lib.load()
+        b = inputs.shape[0]
+        if tuple(inputs.shape[1:]) != (self.in_chan, H, W):
+            raise ValueError(f"inputs must be (B,{self.in_chan},{H},{W})")
+        mask3 = mask.reshape(b, H, W)
+        inputs = inputs.contiguous().float()
+        case_params = case_params.contiguous().float()
+        mask3 = mask3.contiguous().float()
+        pk = self._pack()
+        ws, _ = self._workspace(b)
+        nbytes = lib.fno_rollout_host_scratch_bytes(b, self.n_case_params, steps)
+        key = ("host_io", b, steps)
+        ent = self._ws_cache.get(key)
+        if ent is None:
+            dev_io = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
+            out = torch.empty(steps, b, self.out_chan, H, W, dtype=torch.float32).pin_memory()
+            ent = (dev_io, out)
+            self._ws_cache[key] = ent
+        dev_io, out = ent
+        _lib.check(lib.fno_rollout_host(C.byref(pk["struct"]), inputs.data_ptr(), mask3.data_ptr(),
+                                        case_params.data_ptr(), out.data_ptr(), steps, C.byref(ws), dev_io.data_ptr(),
+                                        b, self._act_code(), self._stream()), "fno_rollout_host")
+        torch.cuda.current_stream(self.device).synchronize()
+        return out

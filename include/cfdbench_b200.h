@@ -1,0 +1,170 @@
+/* cfdbench_b200 -- C ABI of the B200-native FNO hot path for CFDBench.
+ *
+ * The reference (luo-yining/CFDBench @ 6c30c62) is pure Python/PyTorch: its "FFI" for this path is the
+ * set of ATen calls made by src/models/fno/fno2d.py.  Each entry point below replaces the calls cited
+ * next to it.  All pointers are raw device pointers unless a name ends in _host; buffers are owned by the
+ * caller (PyTorch's allocator in the Python wrapper); every call is asynchronous on `stream`
+ * (a cudaStream_t passed as void*) and returns 0 on success, non-zero otherwise
+ * (fno_last_error() gives the message).  No entry point synchronises the device, none falls back to CPU.
+ *
+ * Fixed configuration (the reference's FNO config, src/args.py:99-103,187-197): H=W=64, hidden=32,
+ * modes 12x12, fc1 width 128, out_chan=2, in_chan=2.  Activation storage `act_dtype`:
+ * FNO_ACT_F32 (parity mode) or FNO_ACT_BF16 (hidden activations stored as bf16 between kernels);
+ * arithmetic is fp32 in both.
+ *
+ * Layouts
+ *   activations      [B][32][64][64]   act_dtype, NCHW contiguous
+ *   frames / preds   [B][2][64][64]    float32
+ *   mask             [B][64][64]       float32  (a (B,1,64,64) tensor has the same layout)
+ *   case_params      [B][p]            float32
+ *   modes (xm, ym)   [B][288][32]      complex64 (interleaved re,im); mode k = kxi*12 + ky,
+ *                                      kxi 0..11 <-> kx 0..11 (weights1), kxi 12..23 <-> kx 52..63 (weights2)
+ *   packed spectral  [288][32 in][32 out] complex64 (fno_pack_spectral_weights)
+ *   w0t              [32 in][32 out]   float32  (transpose of the Conv2d weight (out,in,1,1))
+ */
+#ifndef CFDBENCH_B200_H_
+#define CFDBENCH_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FNO_ABI_VERSION 1
+#define FNO_MAX_LAYERS 8
+
+enum { FNO_ACT_F32 = 0, FNO_ACT_BF16 = 1 };
+/* epilogues of fno_block_out */
+enum { FNO_EPI_GELU = 0, FNO_EPI_GELU_SAVE_PRE = 1, FNO_EPI_MUL_DGELU = 2, FNO_EPI_PLAIN = 3 };
+
+/* Device-side weights of one model, in kernel layouts (built by the fno_pack_* calls). */
+typedef struct fno_weights {
+  int32_t n_layers;      /* reference fno_depth (4) */
+  int32_t n_case_params; /* p: 5 cavity, 8 cylinder (reference src/utils/autoregressive.py:31-37) */
+  const float* fc0_w;    /* [32][5+p]  fc0.weight  (reference fno2d.py:150-156) */
+  const float* fc0_b;    /* [32] */
+  const void* spec_wk[FNO_MAX_LAYERS]; /* packed blocks.{l}.conv0.weights1/2 */
+  const float* w0t[FNO_MAX_LAYERS];    /* blocks.{l}.w0.weight transposed */
+  const float* w0_b[FNO_MAX_LAYERS];   /* blocks.{l}.w0.bias */
+  const float* fc1_w;    /* [128][32] fc1.weight */
+  const float* fc1_b;    /* [128] */
+  const float* fc2_w;    /* [2][128]  fc2.weight */
+  const float* fc2_b;    /* [2] */
+  const float* gx;       /* [64] float32(np.linspace(0,1,64)): x coordinate per row h (fno2d.py:244-255) */
+  const float* gy;       /* [64] y coordinate per column w */
+} fno_weights;
+
+/* Caller-provided scratch for a batch of B samples. */
+typedef struct fno_workspace {
+  void* act[2]; /* two activation buffers, B*32*4096 elements of act_dtype each (ping-pong) */
+  void* xm;     /* B*288*32 complex64 */
+  void* ym;     /* B*288*32 complex64 */
+} fno_workspace;
+
+int fno_version(void);
+const char* fno_last_error(void);
+/* bytes of one activation buffer / one mode buffer for batch B */
+size_t fno_act_bytes(int batch, int act_dtype);
+size_t fno_modes_bytes(int batch);
+
+/* weights1, weights2: (32,32,12,12) complex64 as stored by the reference (fno2d.py:31-51).
+ * conj_transpose=0 -> wk[k][i][o] = W[i][o][k] (forward); 1 -> wk[k][o][i] = conj(W[i][o][k]) (adjoint). */
+int fno_pack_spectral_weights(const void* weights1, const void* weights2, void* wk, int conj_transpose, void* stream);
+/* gradient wrt packed forward weights [288][32][32] -> gradients of weights1 / weights2 */
+int fno_unpack_spectral_grads(const void* gwk, void* gw1, void* gw2, void* stream);
+
+/* Channel assembly + fc0: torch.cat/repeat/get_coords/Conv2d(5+p,32,1) (reference fno2d.py:195-217,244-255) */
+int fno_lift_fwd(const float* inputs, const float* mask, const float* case_params, const fno_weights* w,
+                 void* act_out, int batch, int act_dtype, void* stream);
+
+/* The three phases of SpectralConv2d_fast + FnoBlock (reference fno2d.py:59-82, 106-112):            */
+/* (1) torch.fft.rfft2 restricted to the kept modes (fno2d.py:62,73-78); outputs scaled by s0 (ky=0), s1 (ky>0) */
+int fno_spectral_dft_fwd(const void* act_in, void* xm, int batch, int act_dtype, float s0, float s1, void* stream);
+/* (2) einsum("bixy,ioxy->boxy") on both corners (fno2d.py:54-57,73-78) */
+int fno_mode_mix(const void* xm, const void* wk, void* ym, int batch, void* stream);
+/* (3) irfft2 of the zero-padded spectrum (fno2d.py:65-72,81) + Conv2d(32,32,1) + add + GELU (fno2d.py:104-111).
+ *     s0/s1 scale the ky=0 / ky>0 bins (forward: 1/4096, 2/4096).  pre_out/pre_in: see FNO_EPI_*. */
+int fno_block_out(int epilogue, const void* ym, const void* act_in, const float* w0t, const float* bias,
+                  void* act_out, float* pre_out, const float* pre_in, int batch, int act_dtype, float s0, float s1,
+                  void* stream);
+/* all three: act_out = FnoBlock_l(act_in) */
+int fno_block_fwd(const fno_weights* w, int layer, const void* act_in, void* act_out, float* pre_out,
+                  const fno_workspace* ws, int batch, int act_dtype, void* stream);
+
+/* fc1 + GELU + fc2 + "* mask" (reference fno2d.py:228-233) */
+int fno_project_fwd(const void* act_in, const float* mask, const fno_weights* w, float* preds, int batch,
+                    int act_dtype, void* stream);
+
+/* Fno2d.forward without the loss (reference fno2d.py:178-233): preds[B][2][64][64] */
+int fno_forward(const fno_weights* w, const float* inputs, const float* mask, const float* case_params,
+                float* preds, const fno_workspace* ws, int batch, int act_dtype, void* stream);
+
+/* Fno2d.generate_many (reference fno2d.py:269-295): preds_seq[steps][B][2][64][64], step s feeds step s+1 */
+int fno_rollout(const fno_weights* w, const float* inputs, const float* mask, const float* case_params,
+                float* preds_seq, int steps, const fno_workspace* ws, int batch, int act_dtype, void* stream);
+
+/* Same, with HOST buffers (pinned or pageable): copies inputs/mask/case_params to the device scratch
+ * frames `dev_io` (caller-provided: (2 + 1 + steps*2)*B*4096*4 + B*p*4 bytes), runs the rollout and copies
+ * preds_seq back; returns after the D2H copy has been enqueued (synchronise the stream to read). */
+int fno_rollout_host(const fno_weights* w, const float* inputs_host, const float* mask_host,
+                     const float* case_params_host, float* preds_seq_host, int steps, const fno_workspace* ws,
+                     void* dev_io, int batch, int act_dtype, void* stream);
+size_t fno_rollout_host_scratch_bytes(int batch, int n_case_params, int steps);
+
+/* ---------------------------------------------------------------------------------------------------
+ * Training step (what torch.autograd derives for loss["nmse"].backward(), reference src/train_auto.py:255)
+ * ------------------------------------------------------------------------------------------------- */
+
+/* Buffers the forward pass leaves for the backward pass (caller-allocated, batch B). */
+typedef struct fno_train_saved {
+  void* act[FNO_MAX_LAYERS + 1]; /* a_0 (lift output) .. a_L (last block output), act_dtype */
+  float* pre[FNO_MAX_LAYERS];    /* pre-activation of each block, float32 [B][32][64][64] */
+  void* xm[FNO_MAX_LAYERS];      /* kept modes of a_l, complex64 [B][288][32] */
+} fno_train_saved;
+
+/* Extra weight views the backward pass needs. */
+typedef struct fno_weights_bwd {
+  const void* spec_wkT[FNO_MAX_LAYERS]; /* fno_pack_spectral_weights(..., conj_transpose=1) */
+  const float* w0[FNO_MAX_LAYERS];      /* blocks.{l}.w0.weight in its natural [out][in] layout */
+} fno_weights_bwd;
+
+/* Gradient outputs, reference parameter layouts (float32 / complex64). All are overwritten. */
+typedef struct fno_grads {
+  float* fc0_w; /* [32][5+p] */
+  float* fc0_b; /* [32] */
+  void* spec_w1[FNO_MAX_LAYERS]; /* (32,32,12,12) complex64 */
+  void* spec_w2[FNO_MAX_LAYERS];
+  float* w0_w[FNO_MAX_LAYERS]; /* [32][32] */
+  float* w0_b[FNO_MAX_LAYERS]; /* [32] */
+  float* fc1_w; /* [128][32] */
+  float* fc1_b; /* [128] */
+  float* fc2_w; /* [2][128] */
+  float* fc2_b; /* [2] */
+} fno_grads;
+
+/* Scratch of the backward pass. */
+typedef struct fno_bwd_scratch {
+  float* d[2];   /* two float32 [B][32][64][64] gradient buffers (ping-pong) */
+  float* dz1;    /* float32 [min(B,FNO_BWD_CHUNK)][128][64][64] */
+  void* gm;      /* complex64 [B][288][32]: scaled modes of the block's upstream gradient */
+  void* gwk;     /* complex64 [288][32][32] */
+} fno_bwd_scratch;
+#define FNO_BWD_CHUNK 32
+
+/* Fno2d.forward (reference fno2d.py:178-233) that also fills `saved`. ws->ym is used as scratch. */
+int fno_forward_train(const fno_weights* w, const float* inputs, const float* mask, const float* case_params,
+                      float* preds, const fno_train_saved* saved, const fno_workspace* ws, int batch,
+                      int act_dtype, void* stream);
+
+/* Backward of the above given dL/dpreds (float32 [B][2][64][64]); fills `grads`. */
+int fno_backward(const fno_weights* w, const fno_weights_bwd* wb, const float* inputs, const float* mask,
+                 const float* case_params, const float* dpreds, const fno_train_saved* saved,
+                 const fno_grads* grads, const fno_bwd_scratch* scratch, const fno_workspace* ws, int batch,
+                 int act_dtype, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CFDBENCH_B200_H_ */
