@@ -94,17 +94,18 @@ def test_mode_mix_and_pack_kernels(lib):
     w1, w2 = sd["blocks.0.conv0.weights1"], sd["blocks.0.conv0.weights2"]
     xm = (rng.standard_normal((batch, 288, 32)) + 1j * rng.standard_normal((batch, 288, 32))).astype(np.complex64)
     wk = torch.empty(288, 32, 32, dtype=torch.complex64, device="cuda")
-    _lib.check(lib.fno_pack_spectral_weights(dev(w1).data_ptr(), dev(w2).data_ptr(), wk.data_ptr(), 0, stream()), "pack")
+    w1d, w2d, xmd = dev(w1), dev(w2), dev(xm)  # keep alive: the calls are asynchronous
+    _lib.check(lib.fno_pack_spectral_weights(w1d.data_ptr(), w2d.data_ptr(), wk.data_ptr(), 0, stream()), "pack")
     wt = onp.stack_weights(w1, w2).reshape(32, 32, 288)  # [i][o][k]
     np.testing.assert_array_equal(wk.cpu().numpy(), wt.transpose(2, 0, 1).astype(np.complex64))
     ym = torch.zeros(batch, 288, 32, dtype=torch.complex64, device="cuda")
-    _lib.check(lib.fno_mode_mix(dev(xm).data_ptr(), wk.data_ptr(), ym.data_ptr(), batch, stream()), "mix")
+    _lib.check(lib.fno_mode_mix(xmd.data_ptr(), wk.data_ptr(), ym.data_ptr(), batch, stream()), "mix")
     ref = np.einsum("bki,iok->bko", xm.astype(np.complex128), wt)
     err = np.linalg.norm(ym.cpu().numpy() - ref) / np.linalg.norm(ref)
     assert err < 2e-6, err
     # adjoint pack + unpack
     wkT = torch.empty(288, 32, 32, dtype=torch.complex64, device="cuda")
-    _lib.check(lib.fno_pack_spectral_weights(dev(w1).data_ptr(), dev(w2).data_ptr(), wkT.data_ptr(), 1, stream()), "packT")
+    _lib.check(lib.fno_pack_spectral_weights(w1d.data_ptr(), w2d.data_ptr(), wkT.data_ptr(), 1, stream()), "packT")
     np.testing.assert_array_equal(wkT.cpu().numpy(), np.conj(wt).transpose(2, 1, 0).astype(np.complex64))
     g1 = torch.empty(32, 32, 12, 12, dtype=torch.complex64, device="cuda")
     g2 = torch.empty_like(g1)
@@ -130,10 +131,11 @@ def test_block_out_kernel(lib, epi):
             "plain": _lib.EPI_PLAIN}[epi]
     fwd = epi in ("gelu", "save_pre")
     s0, s1 = (1 / 4096, 2 / 4096) if fwd else (1.0, 1.0)
-    _lib.check(lib.fno_block_out(code, ymd.data_ptr(), dev(x).data_ptr(), dev(w0.T.copy()).data_ptr(),
-                                 dev(bias).data_ptr() if fwd else None, out.data_ptr(),
+    xd, w0td, biasd, pred = dev(x), dev(w0.T.copy()), dev(bias), dev(pre_in)  # keep alive (async launch)
+    _lib.check(lib.fno_block_out(code, ymd.data_ptr(), xd.data_ptr(), w0td.data_ptr(),
+                                 biasd.data_ptr() if fwd else None, out.data_ptr(),
                                  pre_out.data_ptr() if epi == "save_pre" else None,
-                                 dev(pre_in).data_ptr() if epi == "mul_dgelu" else None, batch, _lib.ACT_F32,
+                                 pred.data_ptr() if epi == "mul_dgelu" else None, batch, _lib.ACT_F32,
                                  s0, s1, stream()), "block_out")
     ym_r = ym.astype(np.complex64).astype(np.complex128)
     spec = onp.spectral_inverse(ym_r, 64, 64, 12, 12, c0=None if fwd else 1.0, c1=None if fwd else 1.0)
@@ -159,9 +161,9 @@ def test_lift_and_project_kernels(lib, problem):
     m = make_model(sd, p)
     pk = m._pack()
     a0 = torch.zeros(3, 32, 64, 64, device="cuda")
-    _lib.check(lib.fno_lift_fwd(dev(batch["inputs"]).data_ptr(), dev(batch["mask"]).data_ptr(),
-                                dev(batch["case_params"]).data_ptr(), C.byref(pk["struct"]), a0.data_ptr(), 3,
-                                _lib.ACT_F32, stream()), "lift")
+    inp_d, mk_d, cp_d = dev(batch["inputs"]), dev(batch["mask"]), dev(batch["case_params"])
+    _lib.check(lib.fno_lift_fwd(inp_d.data_ptr(), mk_d.data_ptr(), cp_d.data_ptr(), C.byref(pk["struct"]),
+                                a0.data_ptr(), 3, _lib.ACT_F32, stream()), "lift")
     ref = onp.conv1x1(onp.lift_features(batch["inputs"], batch["case_params"], batch["mask"]),
                       sd["fc0.weight"], sd["fc0.bias"])
     assert rel(a0.cpu().numpy(), ref) < 2e-6
@@ -169,7 +171,8 @@ def test_lift_and_project_kernels(lib, problem):
     rng = np.random.default_rng(7)
     a = rng.standard_normal((3, 32, 64, 64)).astype(np.float32)
     preds = torch.zeros(3, 2, 64, 64, device="cuda")
-    _lib.check(lib.fno_project_fwd(dev(a).data_ptr(), dev(batch["mask"]).data_ptr(), C.byref(pk["struct"]),
+    a_d = dev(a)
+    _lib.check(lib.fno_project_fwd(a_d.data_ptr(), mk_d.data_ptr(), C.byref(pk["struct"]),
                                    preds.data_ptr(), 3, _lib.ACT_F32, stream()), "project")
     z1 = onp.conv1x1(a.astype(np.float64), sd["fc1.weight"], sd["fc1.bias"])
     refp = onp.conv1x1(onp.gelu(z1), sd["fc2.weight"], sd["fc2.bias"]) * batch["mask"]
@@ -183,8 +186,9 @@ def test_gelu_device_accuracy(lib):
     ym = torch.zeros(1, 288, 32, dtype=torch.complex64, device="cuda")
     eye = np.eye(32, dtype=np.float32)
     out = torch.zeros(1, 32, 64, 64, device="cuda")
-    _lib.check(lib.fno_block_out(_lib.EPI_GELU, ym.data_ptr(), dev(xs).data_ptr(), dev(eye).data_ptr(),
-                                 dev(np.zeros(32, np.float32)).data_ptr(), out.data_ptr(), None, None, 1,
+    xs_d, eye_d, zero_d = dev(xs), dev(eye), dev(np.zeros(32, np.float32))
+    _lib.check(lib.fno_block_out(_lib.EPI_GELU, ym.data_ptr(), xs_d.data_ptr(), eye_d.data_ptr(),
+                                 zero_d.data_ptr(), out.data_ptr(), None, None, 1,
                                  _lib.ACT_F32, 1 / 4096, 2 / 4096, stream()), "block_out")
     ref = onp.gelu(xs.astype(np.float64))
     got = out.cpu().numpy().astype(np.float64)
@@ -223,7 +227,8 @@ def test_rollout_matches_reference_golden(name):
     # teacher-forced: step s from the golden frame s-1 (north_star: per-step output on identical inputs)
     for s in range(steps):
         prev = inp if s == 0 else torch.from_numpy(gold[s - 1]).cuda()
-        e = rel(m.generate(prev, cp, mk).cpu().numpy(), gold[s])
+        with torch.no_grad():  # as reference src/test_multistep.py:108
+            e = rel(m.generate(prev, cp, mk).cpu().numpy(), gold[s])
         assert e < TOL, (s, e)
     # free-running: errors compound, allow a 10x margin at the last step
     for s in range(steps):
