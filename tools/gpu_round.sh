@@ -8,7 +8,7 @@ echo "pytest exit $?"; tail -15 gpurun_out/pytest_gpu_$TAG.log | cut -c1-300
 timeout 600 python bench.py --steps 20 --warmup 3 > gpurun_out/bench_$TAG.json 2> gpurun_out/bench_$TAG.err
 echo "bench exit $?"; tail -c 3000 gpurun_out/bench_$TAG.json; tail -3 gpurun_out/bench_$TAG.err
 # launch list of one rollout step (14 launches) after 2 warm-up steps (+ pack kernels: skip 36)
-timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -s 36 -c 14 --csv \
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 64 --csv \
    --log-file gpurun_out/launches_$TAG.csv python tools/prof_driver.py --act bf16 --steps 3 > /dev/null 2>&1
 echo "ncu launches exit $?"; grep -c gpu__time gpurun_out/launches_$TAG.csv
 for K in "$@"; do
