@@ -1,5 +1,6 @@
 // extern "C" surface of libcfdbench_b200.so (declared in include/cfdbench_b200.h).
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "../../include/cfdbench_b200.h"
@@ -14,6 +15,9 @@ cudaError_t launch_unpack_spectral(const void*, void*, void*, cudaStream_t);
 template <typename TAct>
 cudaError_t launch_block_out(int, const void*, const void*, const float*, const float*, void*, float*, const float*,
                              int, float, float, cudaStream_t);
+template <typename TAct>
+cudaError_t launch_block_out_tc(int, const void*, const void*, const float*, const float*, void*, float*,
+                                const float*, int, float, float, cudaStream_t);
 template <typename TAct>
 cudaError_t launch_lift(const float*, const float*, const float*, const float*, const float*, const float*,
                         const float*, void*, int, int, cudaStream_t);
@@ -112,11 +116,22 @@ int fno_block_out(int epilogue, const void* ym, const void* act_in, const float*
     return fail(kErrArg, "fno_block_out: bad argument");
   if (epilogue == FNO_EPI_GELU_SAVE_PRE && !pre_out) return fail(kErrArg, "fno_block_out: pre_out is null");
   if (epilogue == FNO_EPI_MUL_DGELU && !pre_in) return fail(kErrArg, "fno_block_out: pre_in is null");
-  cudaError_t e = act_dtype == FNO_ACT_F32
-                      ? launch_block_out<float>(epilogue, ym, act_in, w0t, bias, act_out, pre_out, pre_in, batch, s0,
-                                                s1, S(stream))
-                      : launch_block_out<__nv_bfloat16>(epilogue, ym, act_in, w0t, bias, act_out, pre_out, pre_in,
-                                                        batch, s0, s1, S(stream));
+  static const bool use_cuda_cores = [] {  // A/B switch while the tensor-core kernel is being validated
+    const char* v = getenv("FNO_BLOCK_OUT_IMPL");
+    return v != nullptr && strcmp(v, "cuda") == 0;
+  }();
+  cudaError_t e;
+  if (use_cuda_cores) {
+    e = act_dtype == FNO_ACT_F32
+            ? launch_block_out<float>(epilogue, ym, act_in, w0t, bias, act_out, pre_out, pre_in, batch, s0, s1, S(stream))
+            : launch_block_out<__nv_bfloat16>(epilogue, ym, act_in, w0t, bias, act_out, pre_out, pre_in, batch, s0, s1,
+                                              S(stream));
+  } else {
+    e = act_dtype == FNO_ACT_F32
+            ? launch_block_out_tc<float>(epilogue, ym, act_in, w0t, bias, act_out, pre_out, pre_in, batch, s0, s1, S(stream))
+            : launch_block_out_tc<__nv_bfloat16>(epilogue, ym, act_in, w0t, bias, act_out, pre_out, pre_in, batch, s0,
+                                                 s1, S(stream));
+  }
   FNO_CUDA(e, "block_out_kernel");
   return kOk;
 }
