@@ -117,7 +117,7 @@ __global__ void __launch_bounds__(kTcThreads, 1)
   const int n_mine = (first < n_items) ? (n_items - first + gridDim.x - 1) / gridDim.x : 0;
   const int n_tiles_total = n_mine * kTcTiles;
 
-  // TMA of global tile index q (= item_iter * 4 + t) into raw stage q & 1, issued by warp 0
+  // TMA of global tile index q (= item_iter * 4 + t) into raw stage q & 1, issued by one whole warp
   auto issue_tile_load = [&](int q) {
     const int item = first + (q / kTcTiles) * gridDim.x;
     const int b = item >> 3, r = item & 7, t = q % kTcTiles;
@@ -131,7 +131,7 @@ __global__ void __launch_bounds__(kTcThreads, 1)
                &sm.raw_bar[s]);
     }
   };
-  if (warp == 0) {
+  if (warp == 1) {
     if (n_tiles_total > 0) issue_tile_load(0);
     if (n_tiles_total > 1) issue_tile_load(1);
   }
@@ -258,32 +258,32 @@ __global__ void __launch_bounds__(kTcThreads, 1)
       __syncthreads();  // operands of tile t complete; raw[s] free; epilogue(t-1) TMEM reads (prev iteration) done
       tc::fence_after_thread_sync();
 
+      if (warp == 1 && q + 2 < n_tiles_total) issue_tile_load(q + 2);
       if (warp == 0) {
-        if (q + 2 < n_tiles_total) issue_tile_load(q + 2);
-        if (lane == 0) {
+        if (tc::elect_one()) {
+          // 3xTF32: pass 0 = hi*hi, pass 1 = lo*hi, pass 2 = hi*lo (A part, B part).  Everything below is
+          // warp-uniform and unrolled, so the descriptors live in uniform registers.
           const uint32_t d_tmem = tmem_base + t * kC;
-          bool acc = false;
-          // pass 0: hi*hi, pass 1: lo*hi, pass 2: hi*lo   (A part, B part)
-#pragma unroll 1
+          const uint32_t a_e[3] = {tc::smem_addr(sm.e_hi), tc::smem_addr(sm.e_lo), tc::smem_addr(sm.e_hi)};
+          const uint32_t b_z[3] = {tc::smem_addr(sm.zb_hi[t]), tc::smem_addr(sm.zb_hi[t]), tc::smem_addr(sm.zb_lo[t])};
+          const uint32_t a_x[3] = {tc::smem_addr(sm.ax_hi[s]), tc::smem_addr(sm.ax_lo[s]), tc::smem_addr(sm.ax_hi[s])};
+          const uint32_t b_w[3] = {tc::smem_addr(sm.wb_hi), tc::smem_addr(sm.wb_hi), tc::smem_addr(sm.wb_lo)};
+#pragma unroll
           for (int pass = 0; pass < 3; ++pass) {
-            const float* ea = (pass == 1) ? sm.e_lo : sm.e_hi;
-            const float* zb = (pass == 2) ? sm.zb_lo[t] : sm.zb_hi[t];
+            const uint64_t da0 = tc::make_smem_desc(a_e[pass], kLboA, 128);
+            const uint64_t db0 = tc::make_smem_desc(b_z[pass], kLboB, 128);
 #pragma unroll
             for (int ks = 0; ks < kKE / 8; ++ks) {
-              const uint64_t da = tc::make_smem_desc(tc::smem_addr(ea) + ks * 2 * kLboA, kLboA, 128);
-              const uint64_t db = tc::make_smem_desc(tc::smem_addr(zb) + ks * 2 * kLboB, kLboB, 128);
-              tc::mma_tf32(d_tmem, da, db, idesc, acc);
-              acc = true;
+              const uint64_t da = da0 + ((ks * 2 * kLboA) >> 4), db = db0 + ((ks * 2 * kLboB) >> 4);
+              if (pass == 0 && ks == 0) tc::mma_tf32_imm<false>(d_tmem, da, db, idesc);
+              else tc::mma_tf32_imm<true>(d_tmem, da, db, idesc);
             }
             if (kBf16 && pass == 1) continue;  // conv-part A has no lo component
-            const float* xa = (pass == 1) ? sm.ax_lo[s] : sm.ax_hi[s];
-            const float* wb = (pass == 2) ? sm.wb_lo : sm.wb_hi;
+            const uint64_t dx0 = tc::make_smem_desc(a_x[pass], kLboA, 128);
+            const uint64_t dw0 = tc::make_smem_desc(b_w[pass], kLboB, 128);
 #pragma unroll
-            for (int ks = 0; ks < kKConv / 8; ++ks) {
-              const uint64_t da = tc::make_smem_desc(tc::smem_addr(xa) + ks * 2 * kLboA, kLboA, 128);
-              const uint64_t db = tc::make_smem_desc(tc::smem_addr(wb) + ks * 2 * kLboB, kLboB, 128);
-              tc::mma_tf32(d_tmem, da, db, idesc, true);
-            }
+            for (int ks = 0; ks < kKConv / 8; ++ks)
+              tc::mma_tf32_imm<true>(d_tmem, dx0 + ((ks * 2 * kLboA) >> 4), dw0 + ((ks * 2 * kLboB) >> 4), idesc);
           }
           tc::mma_commit(&sm.mma_bar[t]);
         }
