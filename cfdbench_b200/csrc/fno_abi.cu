@@ -25,6 +25,9 @@ template <typename TAct>
 cudaError_t launch_project(const void*, const float*, const float*, const float*, const float*, const float*, float*,
                            int, cudaStream_t);
 template <typename TAct>
+cudaError_t launch_project_tc(const void*, const float*, const float*, const float*, const float*, const float*,
+                              float*, int, cudaStream_t);
+template <typename TAct>
 cudaError_t launch_project_bwd(const void*, const float*, const float*, const float*, const float*, const float*,
                                const float*, float*, float*, float*, float*, float*, int, cudaStream_t);
 template <typename TP, typename TQ, int NJ, int NI>
@@ -150,10 +153,20 @@ int fno_project_fwd(const void* act_in, const float* mask, const fno_weights* w,
                     int act_dtype, void* stream) {
   if (!act_in || !mask || !w || !preds || batch <= 0 || bad_dtype(act_dtype))
     return fail(kErrArg, "fno_project_fwd: bad argument");
-  cudaError_t e = act_dtype == FNO_ACT_F32
-                      ? launch_project<float>(act_in, w->fc1_w, w->fc1_b, w->fc2_w, w->fc2_b, mask, preds, batch, S(stream))
-                      : launch_project<__nv_bfloat16>(act_in, w->fc1_w, w->fc1_b, w->fc2_w, w->fc2_b, mask, preds,
-                                                      batch, S(stream));
+  static const bool use_cuda_cores = [] {  // A/B switch while the tensor-core kernel is being validated
+    const char* v = getenv("FNO_PROJECT_IMPL");
+    return v != nullptr && strcmp(v, "cuda") == 0;
+  }();
+  cudaError_t e;
+  if (use_cuda_cores) {
+    e = act_dtype == FNO_ACT_F32
+            ? launch_project<float>(act_in, w->fc1_w, w->fc1_b, w->fc2_w, w->fc2_b, mask, preds, batch, S(stream))
+            : launch_project<__nv_bfloat16>(act_in, w->fc1_w, w->fc1_b, w->fc2_w, w->fc2_b, mask, preds, batch, S(stream));
+  } else {
+    e = act_dtype == FNO_ACT_F32
+            ? launch_project_tc<float>(act_in, w->fc1_w, w->fc1_b, w->fc2_w, w->fc2_b, mask, preds, batch, S(stream))
+            : launch_project_tc<__nv_bfloat16>(act_in, w->fc1_w, w->fc1_b, w->fc2_w, w->fc2_b, mask, preds, batch, S(stream));
+  }
   FNO_CUDA(e, "project_kernel");
   return kOk;
 }

@@ -1,0 +1,227 @@
+// Project kernel on the tensor cores: preds = (fc2 . GELU . fc1)(a_L) * mask
+// replacing Conv2d(32,128,1) + GELU + Conv2d(128,2,1) + "* mask" (reference src/models/fno/fno2d.py:228-233).
+//
+// fc1 is the one genuinely dense GEMM of the model (16.8 MFMA per sample): per tile of 128 pixels
+//     D[128 px][128 hidden] = A[128 px][32 ch] * W1^T         (tcgen05.mma kind::tf32, M=128, N=128, K=32)
+// run as 3xTF32 (hi*hi + lo*hi + hi*lo, round-to-nearest split) so the result stays within 1e-6 of fp32.
+// The (B,128,64,64) hidden tensor of the reference (537 MB at B=256) lives only in TMEM: the epilogue reads
+// it back (thread = pixel, 32 hidden units per warp group), adds the bias, applies the exact GELU, contracts
+// with fc2 in registers and reduces the four column groups through shared-memory atomics.
+//
+// Persistent CTA (512 threads) per SM.  Per tile: the activation values prefetched into registers one tile
+// ahead (coalesced 16-byte loads) are split into tf32 hi/lo and written as the K-major A operand (double
+// buffered); one elected thread issues the 12 MMAs into one of two 128-column TMEM accumulators; the epilogue
+// of the previous tile overlaps them.
+#include "fno_common.cuh"
+#include "tc_common.cuh"
+
+namespace fno {
+
+constexpr int kPtThreads = 512;
+constexpr int kPtM = 128;                                  // pixels per tile (2 image rows)
+constexpr uint32_t kPtLboA = (kPtM / 8) * 128;             // 2048
+constexpr uint32_t kPtLboB = (kProj / 8) * 128;            // 2048 (B operand has 128 rows = hidden units)
+constexpr int kPtTilesPerSample = kHW / kPtM;              // 32
+
+struct PtSmem {
+  alignas(128) float a_hi[2][kPtM * kC];     // 2 x 16 KB
+  alignas(128) float a_lo[2][kPtM * kC];     // 2 x 16 KB
+  alignas(128) float w_hi[kProj * kC];       // 16 KB   B operand: [n = hidden j][k = channel i]
+  alignas(128) float w_lo[kProj * kC];       // 16 KB
+  alignas(16) float4 w2q[kProj / 2];         // (w2[0][j], w2[1][j], w2[0][j+1], w2[1][j+1])
+  alignas(16) float b1[kProj];
+  alignas(16) float2 osum[2][kPtM];          // fc2 partial sums per pixel, double buffered
+  alignas(8) uint64_t mma_bar[2];
+  uint32_t tmem_base;
+};
+
+// Activation values of one tile held by a thread between the prefetch and the split pass.
+// task = rep*512 + tid -> (pixel m = task & 127, channel quad kq = task >> 7): lanes run over consecutive pixels,
+// so the global loads coalesce (128 B per channel per warp) and the 16-byte operand stores are conflict-free.
+template <typename TAct>
+struct PtRegs {
+  TAct v[2][4];
+};
+
+template <typename TAct>
+__device__ __forceinline__ void pt_prefetch(PtRegs<TAct>& r, const TAct* __restrict__ a, int tile, int tid) {
+  const int b = tile / kPtTilesPerSample, p0 = (tile % kPtTilesPerSample) * kPtM;
+#pragma unroll
+  for (int rep = 0; rep < 2; ++rep) {
+    const int task = rep * kPtThreads + tid;
+    const int m = task & (kPtM - 1), kq = task >> 7;
+    const TAct* src = a + (static_cast<size_t>(b) * kC + 4 * kq) * kHW + p0 + m;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) r.v[rep][c] = __ldg(src + static_cast<size_t>(c) * kHW);
+  }
+}
+
+__device__ __forceinline__ float pt_to_float(float v) { return v; }
+__device__ __forceinline__ float pt_to_float(__nv_bfloat16 v) { return __bfloat162float(v); }
+
+template <typename TAct>
+__device__ __forceinline__ void pt_split_store(const PtRegs<TAct>& r, float* a_hi, float* a_lo, int tid) {
+#pragma unroll
+  for (int rep = 0; rep < 2; ++rep) {
+    const int task = rep * kPtThreads + tid;
+    const int m = task & (kPtM - 1), kq = task >> 7;
+    float hi[4], lo[4];
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      const float x = pt_to_float(r.v[rep][c]);
+      if constexpr (sizeof(TAct) == 4) tc::split_tf32(x, hi[c], lo[c]);
+      else hi[c] = x;  // bf16 is tf32-exact: no lo part
+    }
+    const uint32_t off = tc::kmajor_offset(m, 4 * kq, kPtM) / 4;
+    *reinterpret_cast<float4*>(a_hi + off) = make_float4(hi[0], hi[1], hi[2], hi[3]);
+    if constexpr (sizeof(TAct) == 4) *reinterpret_cast<float4*>(a_lo + off) = make_float4(lo[0], lo[1], lo[2], lo[3]);
+  }
+}
+
+template <typename TAct>
+__global__ void __launch_bounds__(kPtThreads, 1)
+    project_tc_kernel(const TAct* __restrict__ a, const float* __restrict__ w1, const float* __restrict__ b1,
+                      const float* __restrict__ w2, const float* __restrict__ b2, const float* __restrict__ mask,
+                      float* __restrict__ preds, int n_tiles) {
+  extern __shared__ unsigned char smem_raw[];
+  PtSmem& sm = *reinterpret_cast<PtSmem*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~static_cast<uintptr_t>(127));
+  constexpr bool kBf16 = sizeof(TAct) == 2;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+  if (tid == 0) {
+    mbar_init(&sm.mma_bar[0], 1);
+    mbar_init(&sm.mma_bar[1], 1);
+    fence_mbar_init();
+  }
+  if (warp == 0) tc::tmem_alloc<2 * kProj>(&sm.tmem_base);
+  for (int e = tid; e < kProj * kC; e += kPtThreads) {  // w1[j][i] -> B[n = j][k = i]
+    const int j = e / kC, i = e % kC;
+    float hi, lo;
+    tc::split_tf32(w1[e], hi, lo);
+    const uint32_t off = tc::kmajor_offset(j, i, kProj) / 4;
+    sm.w_hi[off] = hi;
+    sm.w_lo[off] = lo;
+  }
+  if (tid < kProj / 2) sm.w2q[tid] = make_float4(w2[2 * tid], w2[kProj + 2 * tid], w2[2 * tid + 1], w2[kProj + 2 * tid + 1]);
+  if (tid < kProj) sm.b1[tid] = b1[tid];
+  const float b2x = b2[0], b2y = b2[1];
+  if (tid < 2 * kPtM) (&sm.osum[0][0])[tid] = make_float2(b2x, b2y);
+  tc::fence_proxy_async_smem();
+  tc::fence_before_thread_sync();
+  __syncthreads();
+  tc::fence_after_thread_sync();
+  const uint32_t tmem_base = sm.tmem_base;
+  constexpr uint32_t idesc = tc::make_idesc_tf32(kPtM, kProj);
+
+  const int first = blockIdx.x, stride = gridDim.x;
+  const int n_mine = (first < n_tiles) ? (n_tiles - first + stride - 1) / stride : 0;
+
+  // epilogue of local tile index `it` (global tile `tile`): TMEM accumulator -> GELU -> fc2 partials
+  auto epilogue = [&](int it) {
+    const int buf = it & 1;
+    mbar_wait(&sm.mma_bar[buf], (it >> 1) & 1);
+    tc::fence_after_thread_sync();
+    const int quad = warp & 3, grp = warp >> 2;  // TMEM lane quadrant / 32-column group
+    float v[32];
+    tc::tmem_ld32(tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + buf * kProj + grp * 32, v);
+    float2 acc = make_float2(0.f, 0.f);  // (out channel 0, out channel 1)
+#pragma unroll
+    for (int c = 0; c < 32; c += 2) {
+      const int j = grp * 32 + c;
+      const float2 bb = *reinterpret_cast<const float2*>(&sm.b1[j]);
+      const float2 g = gelu_erf2(make_float2(v[c] + bb.x, v[c + 1] + bb.y));
+      const float4 wq = sm.w2q[j >> 1];
+      acc = __ffma2_rn(make_float2(g.x, g.x), make_float2(wq.x, wq.y), acc);
+      acc = __ffma2_rn(make_float2(g.y, g.y), make_float2(wq.z, wq.w), acc);
+    }
+    const int m = quad * 32 + lane;
+    atomicAdd(&sm.osum[buf][m].x, acc.x);
+    atomicAdd(&sm.osum[buf][m].y, acc.y);
+    tc::fence_before_thread_sync();
+  };
+  // after the barrier that follows epilogue(it): write tile `it`'s predictions and re-arm its accumulator slot
+  auto finalize = [&](int it) {
+    if (tid < kPtM) {
+      const int buf = it & 1;
+      const int tile = first + it * stride;
+      const int b = tile / kPtTilesPerSample, pix = (tile % kPtTilesPerSample) * kPtM + tid;
+      const float2 s = sm.osum[buf][tid];
+      const float mk = __ldg(mask + static_cast<size_t>(b) * kHW + pix);
+      preds[(static_cast<size_t>(b) * 2 + 0) * kHW + pix] = s.x * mk;
+      preds[(static_cast<size_t>(b) * 2 + 1) * kHW + pix] = s.y * mk;
+      sm.osum[buf][tid] = make_float2(b2x, b2y);
+    }
+  };
+
+  PtRegs<TAct> regs;
+  if (n_mine > 0) pt_prefetch<TAct>(regs, a, first, tid);
+
+  for (int it = 0; it < n_mine; ++it) {
+    const int buf = it & 1;
+    // A[buf] was last read by the MMAs of tile it-2, whose completion epilogue(it-2) waited for
+    pt_split_store<TAct>(regs, sm.a_hi[buf], sm.a_lo[buf], tid);
+    if (it + 1 < n_mine) pt_prefetch<TAct>(regs, a, first + (it + 1) * stride, tid);
+    tc::fence_proxy_async_smem();
+    tc::fence_before_thread_sync();
+    __syncthreads();
+    tc::fence_after_thread_sync();
+    if (it >= 2) finalize(it - 2);  // its atomics completed before the barrier above
+    if (warp == 0) {
+      if (tc::elect_one()) {
+        const uint32_t d_tmem = tmem_base + buf * kProj;
+        const uint32_t a_s[3] = {tc::smem_addr(sm.a_hi[buf]), tc::smem_addr(sm.a_lo[buf]), tc::smem_addr(sm.a_hi[buf])};
+        const uint32_t b_s[3] = {tc::smem_addr(sm.w_hi), tc::smem_addr(sm.w_hi), tc::smem_addr(sm.w_lo)};
+#pragma unroll
+        for (int pass = 0; pass < 3; ++pass) {
+          if (kBf16 && pass == 1) continue;
+          const uint64_t da0 = tc::make_smem_desc(a_s[pass], kPtLboA, 128);
+          const uint64_t db0 = tc::make_smem_desc(b_s[pass], kPtLboB, 128);
+#pragma unroll
+          for (int ks = 0; ks < kC / 8; ++ks) {
+            const uint64_t da = da0 + ((ks * 2 * kPtLboA) >> 4), db = db0 + ((ks * 2 * kPtLboB) >> 4);
+            if (pass == 0 && ks == 0) tc::mma_tf32_imm<false>(d_tmem, da, db, idesc);
+            else tc::mma_tf32_imm<true>(d_tmem, da, db, idesc);
+          }
+        }
+        tc::mma_commit(&sm.mma_bar[buf]);
+      }
+      __syncwarp();
+    }
+    if (it >= 1) epilogue(it - 1);
+  }
+  if (n_mine >= 1) epilogue(n_mine - 1);
+  tc::fence_before_thread_sync();
+  __syncthreads();
+  tc::fence_after_thread_sync();
+  if (n_mine >= 2) finalize(n_mine - 2);
+  if (n_mine >= 1) finalize(n_mine - 1);
+  if (warp == 0) tc::tmem_dealloc<2 * kProj>(tmem_base);
+}
+
+template <typename TAct>
+cudaError_t launch_project_tc(const void* a, const float* w1, const float* b1, const float* w2, const float* b2,
+                              const float* mask, float* preds, int batch, cudaStream_t stream) {
+  auto kern = project_tc_kernel<TAct>;
+  constexpr size_t smem = sizeof(PtSmem) + 128;
+  static bool configured = false;
+  static int n_sm = 0;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    e = cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
+    if (e != cudaSuccess) return e;
+    configured = true;
+  }
+  const int n_tiles = batch * kPtTilesPerSample;
+  const int grid = n_tiles < n_sm ? n_tiles : n_sm;
+  kern<<<grid, kPtThreads, smem, stream>>>(static_cast<const TAct*>(a), w1, b1, w2, b2, mask, preds, n_tiles);
+  return cudaGetLastError();
+}
+template cudaError_t launch_project_tc<float>(const void*, const float*, const float*, const float*, const float*,
+                                              const float*, float*, int, cudaStream_t);
+template cudaError_t launch_project_tc<__nv_bfloat16>(const void*, const float*, const float*, const float*,
+                                                      const float*, const float*, float*, int, cudaStream_t);
+
+}  // namespace fno
