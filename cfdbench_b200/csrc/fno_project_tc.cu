@@ -6,7 +6,7 @@
 // run as 3xTF32 (hi*hi + lo*hi + hi*lo, round-to-nearest split) so the result stays within 1e-6 of fp32.
 // The (B,128,64,64) hidden tensor of the reference (537 MB at B=256) lives only in TMEM: the epilogue reads
 // it back (thread = pixel, 32 hidden units per warp group), adds the bias, applies the exact GELU, contracts
-// with fc2 in registers and reduces the four column groups through shared-memory atomics.
+// with fc2 in registers; the four column groups are summed in a fixed order (deterministic results).
 //
 // Persistent CTA (512 threads) per SM.  Per tile: the activation values prefetched into registers one tile
 // ahead (coalesced 16-byte loads) are split into tf32 hi/lo and written as the K-major A operand (double
@@ -30,7 +30,7 @@ struct PtSmem {
   alignas(128) float w_lo[kProj * kC];       // 16 KB
   alignas(16) float4 w2q[kProj / 2];         // (w2[0][j], w2[1][j], w2[0][j+1], w2[1][j+1])
   alignas(16) float b1[kProj];
-  alignas(16) float2 osum[2][kPtM];          // fc2 partial sums per pixel, double buffered
+  alignas(16) float2 opart[2][4][kPtM];      // fc2 partial sums per (column group, pixel), double buffered
   alignas(8) uint64_t mma_bar[2];
   uint32_t tmem_base;
 };
@@ -105,7 +105,6 @@ __global__ void __launch_bounds__(kPtThreads, 1)
   if (tid < kProj / 2) sm.w2q[tid] = make_float4(w2[2 * tid], w2[kProj + 2 * tid], w2[2 * tid + 1], w2[kProj + 2 * tid + 1]);
   if (tid < kProj) sm.b1[tid] = b1[tid];
   const float b2x = b2[0], b2y = b2[1];
-  if (tid < 2 * kPtM) (&sm.osum[0][0])[tid] = make_float2(b2x, b2y);
   tc::fence_proxy_async_smem();
   tc::fence_before_thread_sync();
   __syncthreads();
@@ -134,9 +133,7 @@ __global__ void __launch_bounds__(kPtThreads, 1)
       acc = __ffma2_rn(make_float2(g.x, g.x), make_float2(wq.x, wq.y), acc);
       acc = __ffma2_rn(make_float2(g.y, g.y), make_float2(wq.z, wq.w), acc);
     }
-    const int m = quad * 32 + lane;
-    atomicAdd(&sm.osum[buf][m].x, acc.x);
-    atomicAdd(&sm.osum[buf][m].y, acc.y);
+    sm.opart[buf][grp][quad * 32 + lane] = acc;  // summed in a fixed order by finalize(): deterministic
     tc::fence_before_thread_sync();
   };
   // after the barrier that follows epilogue(it): write tile `it`'s predictions and re-arm its accumulator slot
@@ -145,11 +142,12 @@ __global__ void __launch_bounds__(kPtThreads, 1)
       const int buf = it & 1;
       const int tile = first + it * stride;
       const int b = tile / kPtTilesPerSample, pix = (tile % kPtTilesPerSample) * kPtM + tid;
-      const float2 s = sm.osum[buf][tid];
+      const float2 p0 = sm.opart[buf][0][tid], p1 = sm.opart[buf][1][tid], p2 = sm.opart[buf][2][tid],
+                   p3 = sm.opart[buf][3][tid];
+      const float sx = ((b2x + p0.x) + p1.x) + (p2.x + p3.x), sy = ((b2y + p0.y) + p1.y) + (p2.y + p3.y);
       const float mk = __ldg(mask + static_cast<size_t>(b) * kHW + pix);
-      preds[(static_cast<size_t>(b) * 2 + 0) * kHW + pix] = s.x * mk;
-      preds[(static_cast<size_t>(b) * 2 + 1) * kHW + pix] = s.y * mk;
-      sm.osum[buf][tid] = make_float2(b2x, b2y);
+      preds[(static_cast<size_t>(b) * 2 + 0) * kHW + pix] = sx * mk;
+      preds[(static_cast<size_t>(b) * 2 + 1) * kHW + pix] = sy * mk;
     }
   };
 
