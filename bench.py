@@ -111,8 +111,8 @@ def timed_rollout(model, inp, cp, mk, steps: int, warmup: int):
     """K steps = one native rollout of K steps on torch's current stream, CUDA events around it."""
     dev = model.device
     t_spin = time.perf_counter()  # bring the SM clocks up from idle before the contract's W warm-up steps
-    while time.perf_counter() - t_spin < 0.4:
-        model.generate_many(inp, cp, mk, 4)
+    while time.perf_counter() - t_spin < 0.4:  # same `steps` as the timed call: its output buffer gets cached
+        model.generate_many(inp, cp, mk, steps)
         torch.cuda.synchronize(dev)
     for _ in range(max(warmup, 0)):
         model.generate_many(inp, cp, mk, 1)

@@ -25,7 +25,7 @@ __device__ __forceinline__ void gelu_both(float x, float& g, float& dg) {
   const float e = 0.5f * erfc_abs_scaled(ax);  // 0.5 erfc(|x|/sqrt2)
   g = fmaxf(x, 0.f) - ax * e;
   const float cdf = x >= 0.f ? 1.f - e : e;
-  const float pdf = 0.3989422804014327f * exp2f(-0.7213475204444817f * x * x);
+  const float pdf = 0.3989422804014327f * ex2_approx(-0.7213475204444817f * x * x);
   dg = fmaf(x, pdf, cdf);
 }
 

@@ -77,9 +77,9 @@ __global__ void __launch_bounds__(kTcThreads, 1)
                         const float* __restrict__ bias, const float* __restrict__ etab, TAct* __restrict__ out,
                         float* __restrict__ pre_out, const float* __restrict__ pre_in, float s0, float s1,
                         int n_items) {
-  extern __shared__ unsigned char smem_raw[];
-  TcSmem<TAct>& sm = *reinterpret_cast<TcSmem<TAct>*>(
-      (reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~static_cast<uintptr_t>(127));
+  extern __shared__ __align__(1024) unsigned char smem_raw[];  // no pointer arithmetic: keeps LDS/STS addressing
+  TcSmem<TAct>& sm = *reinterpret_cast<TcSmem<TAct>*>(smem_raw);
+  if ((smem_u32(smem_raw) & 127u) != 0) __trap();
   constexpr bool kBf16 = sizeof(TAct) == 2;
   constexpr uint32_t kRowBytes = kW * sizeof(TAct);
   constexpr uint32_t kTileBytes = 2 * kC * kRowBytes;

@@ -83,8 +83,9 @@ __global__ void __launch_bounds__(kPtThreads, 1)
     project_tc_kernel(const TAct* __restrict__ a, const float* __restrict__ w1, const float* __restrict__ b1,
                       const float* __restrict__ w2, const float* __restrict__ b2, const float* __restrict__ mask,
                       float* __restrict__ preds, int n_tiles) {
-  extern __shared__ unsigned char smem_raw[];
-  PtSmem& sm = *reinterpret_cast<PtSmem*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~static_cast<uintptr_t>(127));
+  extern __shared__ __align__(1024) unsigned char smem_raw[];  // no pointer arithmetic: keeps LDS/STS addressing
+  PtSmem& sm = *reinterpret_cast<PtSmem*>(smem_raw);
+  if ((smem_u32(smem_raw) & 127u) != 0) __trap();
   constexpr bool kBf16 = sizeof(TAct) == 2;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
