@@ -119,9 +119,9 @@ int fno_block_out(int epilogue, const void* ym, const void* act_in, const float*
     return fail(kErrArg, "fno_block_out: bad argument");
   if (epilogue == FNO_EPI_GELU_SAVE_PRE && !pre_out) return fail(kErrArg, "fno_block_out: pre_out is null");
   if (epilogue == FNO_EPI_MUL_DGELU && !pre_in) return fail(kErrArg, "fno_block_out: pre_in is null");
-  static const bool use_cuda_cores = [] {  // A/B switch while the tensor-core kernel is being validated
+  static const bool use_cuda_cores = [] {  // A/B switch while the tensor-core kernel is being tuned (default: CUDA cores)
     const char* v = getenv("FNO_BLOCK_OUT_IMPL");
-    return v != nullptr && strcmp(v, "cuda") == 0;
+    return !(v != nullptr && strcmp(v, "tc") == 0);
   }();
   cudaError_t e;
   if (use_cuda_cores) {

@@ -17,38 +17,39 @@
 
 namespace fno {
 
-constexpr int kPtThreads = 512;
+constexpr int kPtThreads = 512;                            // two independent 256-thread tile pipelines
+constexpr int kPtGroup = 256;
 constexpr int kPtM = 128;                                  // pixels per tile (2 image rows)
 constexpr uint32_t kPtLboA = (kPtM / 8) * 128;             // 2048
 constexpr uint32_t kPtLboB = (kProj / 8) * 128;            // 2048 (B operand has 128 rows = hidden units)
 constexpr int kPtTilesPerSample = kHW / kPtM;              // 32
 
 struct PtSmem {
-  alignas(128) float a_hi[2][kPtM * kC];     // 2 x 16 KB
-  alignas(128) float a_lo[2][kPtM * kC];     // 2 x 16 KB
+  alignas(128) float a_hi[2][2][kPtM * kC];  // [group][buffer] 4 x 16 KB
+  alignas(128) float a_lo[2][2][kPtM * kC];  // 4 x 16 KB
   alignas(128) float w_hi[kProj * kC];       // 16 KB   B operand: [n = hidden j][k = channel i]
   alignas(128) float w_lo[kProj * kC];       // 16 KB
   alignas(16) float4 w2q[kProj / 2];         // (w2[0][j], w2[1][j], w2[0][j+1], w2[1][j+1])
   alignas(16) float b1[kProj];
-  alignas(16) float2 opart[2][4][kPtM];      // fc2 partial sums per (column group, pixel), double buffered
-  alignas(8) uint64_t mma_bar[2];
+  alignas(16) float2 opart[2][2][2][kPtM];   // [group][buffer][column half][pixel] fc2 partial sums
+  alignas(8) uint64_t mma_bar[2][2];
   uint32_t tmem_base;
 };
 
 // Activation values of one tile held by a thread between the prefetch and the split pass.
-// task = rep*512 + tid -> (pixel m = task & 127, channel quad kq = task >> 7): lanes run over consecutive pixels,
+// task = rep*256 + gtid -> (pixel m = task & 127, channel quad kq = task >> 7): lanes run over consecutive pixels,
 // so the global loads coalesce (128 B per channel per warp) and the 16-byte operand stores are conflict-free.
 template <typename TAct>
 struct PtRegs {
-  TAct v[2][4];
+  TAct v[4][4];
 };
 
 template <typename TAct>
 __device__ __forceinline__ void pt_prefetch(PtRegs<TAct>& r, const TAct* __restrict__ a, int tile, int tid) {
   const int b = tile / kPtTilesPerSample, p0 = (tile % kPtTilesPerSample) * kPtM;
 #pragma unroll
-  for (int rep = 0; rep < 2; ++rep) {
-    const int task = rep * kPtThreads + tid;
+  for (int rep = 0; rep < 4; ++rep) {
+    const int task = rep * kPtGroup + tid;
     const int m = task & (kPtM - 1), kq = task >> 7;
     const TAct* src = a + (static_cast<size_t>(b) * kC + 4 * kq) * kHW + p0 + m;
 #pragma unroll
@@ -62,8 +63,8 @@ __device__ __forceinline__ float pt_to_float(__nv_bfloat16 v) { return __bfloat1
 template <typename TAct>
 __device__ __forceinline__ void pt_split_store(const PtRegs<TAct>& r, float* a_hi, float* a_lo, int tid) {
 #pragma unroll
-  for (int rep = 0; rep < 2; ++rep) {
-    const int task = rep * kPtThreads + tid;
+  for (int rep = 0; rep < 4; ++rep) {
+    const int task = rep * kPtGroup + tid;
     const int m = task & (kPtM - 1), kq = task >> 7;
     float hi[4], lo[4];
 #pragma unroll
@@ -78,6 +79,10 @@ __device__ __forceinline__ void pt_split_store(const PtRegs<TAct>& r, float* a_h
   }
 }
 
+__device__ __forceinline__ void group_barrier(int grp) {  // named barrier of one 256-thread pipeline
+  asm volatile("bar.sync %0, %1;" ::"r"(grp + 1), "n"(kPtGroup) : "memory");
+}
+
 template <typename TAct>
 __global__ void __launch_bounds__(kPtThreads, 1)
     project_tc_kernel(const TAct* __restrict__ a, const float* __restrict__ w1, const float* __restrict__ b1,
@@ -88,13 +93,15 @@ __global__ void __launch_bounds__(kPtThreads, 1)
   if ((smem_u32(smem_raw) & 127u) != 0) __trap();
   constexpr bool kBf16 = sizeof(TAct) == 2;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int grp = warp >> 3;          // pipeline 0 / 1
+  const int gtid = tid & (kPtGroup - 1), gwarp = warp & 7;
 
   if (tid == 0) {
-    mbar_init(&sm.mma_bar[0], 1);
-    mbar_init(&sm.mma_bar[1], 1);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) mbar_init(&sm.mma_bar[i >> 1][i & 1], 1);
     fence_mbar_init();
   }
-  if (warp == 0) tc::tmem_alloc<2 * kProj>(&sm.tmem_base);
+  if (warp == 0) tc::tmem_alloc<4 * kProj>(&sm.tmem_base);
   for (int e = tid; e < kProj * kC; e += kPtThreads) {  // w1[j][i] -> B[n = j][k = i]
     const int j = e / kC, i = e % kC;
     float hi, lo;
@@ -110,65 +117,72 @@ __global__ void __launch_bounds__(kPtThreads, 1)
   tc::fence_before_thread_sync();
   __syncthreads();
   tc::fence_after_thread_sync();
-  const uint32_t tmem_base = sm.tmem_base;
+  const uint32_t tmem_base = sm.tmem_base + grp * (2 * kProj);
   constexpr uint32_t idesc = tc::make_idesc_tf32(kPtM, kProj);
 
+  // tiles of this CTA: first, first+stride, ...; pipeline g takes every other one
   const int first = blockIdx.x, stride = gridDim.x;
-  const int n_mine = (first < n_tiles) ? (n_tiles - first + stride - 1) / stride : 0;
+  const int n_cta = (first < n_tiles) ? (n_tiles - first + stride - 1) / stride : 0;
+  const int n_mine = (n_cta + 1 - grp) / 2;
+  auto tile_of = [&](int it) { return first + (2 * it + grp) * stride; };
 
-  // epilogue of local tile index `it` (global tile `tile`): TMEM accumulator -> GELU -> fc2 partials
+  // epilogue of local tile `it`: TMEM accumulator -> +bias -> GELU -> fc2 partial sums (two 32-column chunks)
   auto epilogue = [&](int it) {
     const int buf = it & 1;
-    mbar_wait(&sm.mma_bar[buf], (it >> 1) & 1);
+    mbar_wait(&sm.mma_bar[grp][buf], (it >> 1) & 1);
     tc::fence_after_thread_sync();
-    const int quad = warp & 3, grp = warp >> 2;  // TMEM lane quadrant / 32-column group
-    float v[32];
-    tc::tmem_ld32(tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + buf * kProj + grp * 32, v);
-    float2 acc = make_float2(0.f, 0.f);  // (out channel 0, out channel 1)
+    const int quad = gwarp & 3, half = gwarp >> 2;  // TMEM lane quadrant / 64-column half
+    float2 acc = make_float2(0.f, 0.f);             // (out channel 0, out channel 1)
 #pragma unroll
-    for (int c = 0; c < 32; c += 2) {
-      const int j = grp * 32 + c;
-      const float2 bb = *reinterpret_cast<const float2*>(&sm.b1[j]);
-      const float2 g = gelu_erf2(make_float2(v[c] + bb.x, v[c + 1] + bb.y));
-      const float4 wq = sm.w2q[j >> 1];
-      acc = __ffma2_rn(make_float2(g.x, g.x), make_float2(wq.x, wq.y), acc);
-      acc = __ffma2_rn(make_float2(g.y, g.y), make_float2(wq.z, wq.w), acc);
+    for (int chunk = 0; chunk < 2; ++chunk) {
+      float v[32];
+      const int j0 = half * 64 + chunk * 32;
+      tc::tmem_ld32(tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + buf * kProj + j0, v);
+#pragma unroll
+      for (int c = 0; c < 32; c += 2) {
+        const int j = j0 + c;
+        const float2 bb = *reinterpret_cast<const float2*>(&sm.b1[j]);
+        const float2 g = gelu_erf2(make_float2(v[c] + bb.x, v[c + 1] + bb.y));
+        const float4 wq = sm.w2q[j >> 1];
+        acc = __ffma2_rn(make_float2(g.x, g.x), make_float2(wq.x, wq.y), acc);
+        acc = __ffma2_rn(make_float2(g.y, g.y), make_float2(wq.z, wq.w), acc);
+      }
     }
-    sm.opart[buf][grp][quad * 32 + lane] = acc;  // summed in a fixed order by finalize(): deterministic
+    sm.opart[grp][buf][half][quad * 32 + lane] = acc;  // summed in a fixed order by finalize(): deterministic
     tc::fence_before_thread_sync();
   };
-  // after the barrier that follows epilogue(it): write tile `it`'s predictions and re-arm its accumulator slot
+  // after the group barrier that follows epilogue(it): write tile `it`'s predictions
   auto finalize = [&](int it) {
-    if (tid < kPtM) {
+    if (gtid < kPtM) {
       const int buf = it & 1;
-      const int tile = first + it * stride;
-      const int b = tile / kPtTilesPerSample, pix = (tile % kPtTilesPerSample) * kPtM + tid;
-      const float2 p0 = sm.opart[buf][0][tid], p1 = sm.opart[buf][1][tid], p2 = sm.opart[buf][2][tid],
-                   p3 = sm.opart[buf][3][tid];
-      const float sx = ((b2x + p0.x) + p1.x) + (p2.x + p3.x), sy = ((b2y + p0.y) + p1.y) + (p2.y + p3.y);
+      const int tile = tile_of(it);
+      const int b = tile / kPtTilesPerSample, pix = (tile % kPtTilesPerSample) * kPtM + gtid;
+      const float2 p0 = sm.opart[grp][buf][0][gtid], p1 = sm.opart[grp][buf][1][gtid];
       const float mk = __ldg(mask + static_cast<size_t>(b) * kHW + pix);
-      preds[(static_cast<size_t>(b) * 2 + 0) * kHW + pix] = sx * mk;
-      preds[(static_cast<size_t>(b) * 2 + 1) * kHW + pix] = sy * mk;
+      preds[(static_cast<size_t>(b) * 2 + 0) * kHW + pix] = ((b2x + p0.x) + p1.x) * mk;
+      preds[(static_cast<size_t>(b) * 2 + 1) * kHW + pix] = ((b2y + p0.y) + p1.y) * mk;
     }
   };
 
   PtRegs<TAct> regs;
-  if (n_mine > 0) pt_prefetch<TAct>(regs, a, first, tid);
+  if (n_mine > 0) pt_prefetch<TAct>(regs, a, tile_of(0), gtid);
 
   for (int it = 0; it < n_mine; ++it) {
     const int buf = it & 1;
     // A[buf] was last read by the MMAs of tile it-2, whose completion epilogue(it-2) waited for
-    pt_split_store<TAct>(regs, sm.a_hi[buf], sm.a_lo[buf], tid);
-    if (it + 1 < n_mine) pt_prefetch<TAct>(regs, a, first + (it + 1) * stride, tid);
+    pt_split_store<TAct>(regs, sm.a_hi[grp][buf], sm.a_lo[grp][buf], gtid);
     tc::fence_proxy_async_smem();
     tc::fence_before_thread_sync();
-    __syncthreads();
+    group_barrier(grp);
     tc::fence_after_thread_sync();
-    if (it >= 2) finalize(it - 2);  // its atomics completed before the barrier above
-    if (warp == 0) {
+    // prefetch AFTER the fence: the membar inside fence.proxy.async would otherwise wait for these loads
+    if (it + 1 < n_mine) pt_prefetch<TAct>(regs, a, tile_of(it + 1), gtid);
+    if (it >= 2) finalize(it - 2);
+    if (gwarp == 0) {
       if (tc::elect_one()) {
         const uint32_t d_tmem = tmem_base + buf * kProj;
-        const uint32_t a_s[3] = {tc::smem_addr(sm.a_hi[buf]), tc::smem_addr(sm.a_lo[buf]), tc::smem_addr(sm.a_hi[buf])};
+        const uint32_t a_s[3] = {tc::smem_addr(sm.a_hi[grp][buf]), tc::smem_addr(sm.a_lo[grp][buf]),
+                                 tc::smem_addr(sm.a_hi[grp][buf])};
         const uint32_t b_s[3] = {tc::smem_addr(sm.w_hi), tc::smem_addr(sm.w_hi), tc::smem_addr(sm.w_lo)};
 #pragma unroll
         for (int pass = 0; pass < 3; ++pass) {
@@ -182,7 +196,7 @@ __global__ void __launch_bounds__(kPtThreads, 1)
             else tc::mma_tf32_imm<true>(d_tmem, da, db, idesc);
           }
         }
-        tc::mma_commit(&sm.mma_bar[buf]);
+        tc::mma_commit(&sm.mma_bar[grp][buf]);
       }
       __syncwarp();
     }
@@ -190,11 +204,13 @@ __global__ void __launch_bounds__(kPtThreads, 1)
   }
   if (n_mine >= 1) epilogue(n_mine - 1);
   tc::fence_before_thread_sync();
-  __syncthreads();
+  group_barrier(grp);
   tc::fence_after_thread_sync();
   if (n_mine >= 2) finalize(n_mine - 2);
   if (n_mine >= 1) finalize(n_mine - 1);
-  if (warp == 0) tc::tmem_dealloc<2 * kProj>(tmem_base);
+  tc::fence_before_thread_sync();
+  __syncthreads();
+  if (warp == 0) tc::tmem_dealloc<4 * kProj>(sm.tmem_base);
 }
 
 template <typename TAct>
