@@ -181,7 +181,7 @@ def kernel_pass(model, inp, cp, mk, steps: int):
         for l in range(model.num_layers):
             timed("dft_fwd", lambda: lib.fno_spectral_dft_fwd(acts[cur].data_ptr(), bufs["xm"].data_ptr(), b, act, 1.0, 1.0, st))
             timed("mode_mix", lambda: lib.fno_mode_mix(bufs["xm"].data_ptr(), w.spec_wk[l], bufs["ym"].data_ptr(), b, st))
-            timed("block_out", lambda: lib.fno_block_out(_lib.EPI_GELU, bufs["ym"].data_ptr(), acts[cur].data_ptr(),
+            timed("block_out", lambda: lib.fno_block_out(_lib.EPI_GELU, bufs["ym"].data_ptr(), bufs["z"].data_ptr(), acts[cur].data_ptr(),
                                                          w.w0t[l], w.w0_b[l], acts[cur ^ 1].data_ptr(), None, None, b,
                                                          act, inv, 2 * inv, st))
             cur ^= 1

@@ -34,7 +34,7 @@ class FnoWeights(C.Structure):
 
 
 class FnoWorkspace(C.Structure):
-    _fields_ = [("act", C.c_void_p * 2), ("xm", C.c_void_p), ("ym", C.c_void_p)]
+    _fields_ = [("act", C.c_void_p * 2), ("xm", C.c_void_p), ("ym", C.c_void_p), ("z", C.c_void_p)]
 
 
 class FnoGrads(C.Structure):
@@ -78,12 +78,13 @@ SIGNATURES = {
     "fno_last_error": (C.c_char_p, []),
     "fno_act_bytes": (C.c_size_t, [_I, _I]),
     "fno_modes_bytes": (C.c_size_t, [_I]),
+    "fno_z_bytes": (C.c_size_t, [_I]),
     "fno_pack_spectral_weights": (C.c_int, [_P, _P, _P, _I, _P]),
     "fno_unpack_spectral_grads": (C.c_int, [_P, _P, _P, _P]),
     "fno_lift_fwd": (C.c_int, [_P, _P, _P, C.POINTER(FnoWeights), _P, _I, _I, _P]),
     "fno_spectral_dft_fwd": (C.c_int, [_P, _P, _I, _I, _F, _F, _P]),
     "fno_mode_mix": (C.c_int, [_P, _P, _P, _I, _P]),
-    "fno_block_out": (C.c_int, [_I, _P, _P, _P, _P, _P, _P, _P, _I, _I, _F, _F, _P]),
+    "fno_block_out": (C.c_int, [_I, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _F, _F, _P]),
     "fno_block_fwd": (C.c_int, [C.POINTER(FnoWeights), _I, _P, _P, _P, C.POINTER(FnoWorkspace), _I, _I, _P]),
     "fno_project_fwd": (C.c_int, [_P, _P, C.POINTER(FnoWeights), _P, _I, _I, _P]),
     "fno_forward": (C.c_int, [C.POINTER(FnoWeights), _P, _P, _P, _P, C.POINTER(FnoWorkspace), _I, _I, _P]),

@@ -18,6 +18,10 @@ cudaError_t launch_block_out(int, const void*, const void*, const float*, const 
 template <typename TAct>
 cudaError_t launch_block_out_tc(int, const void*, const void*, const float*, const float*, void*, float*,
                                 const float*, int, float, float, cudaStream_t);
+cudaError_t launch_inv_kx(const void*, void*, int, float, float, cudaStream_t);
+template <typename TAct>
+cudaError_t launch_block_tc(int, const void*, const void*, const float*, const float*, void*, float*, const float*, int,
+                            cudaStream_t);
 template <typename TAct>
 cudaError_t launch_lift(const float*, const float*, const float*, const float*, const float*, const float*,
                         const float*, void*, int, int, cudaStream_t);
@@ -71,6 +75,7 @@ size_t fno_act_bytes(int batch, int act_dtype) {
   return static_cast<size_t>(batch) * kC * kHW * (act_dtype == FNO_ACT_BF16 ? 2 : 4);
 }
 size_t fno_modes_bytes(int batch) { return static_cast<size_t>(batch) * kModes * kC * sizeof(float2); }
+size_t fno_z_bytes(int batch) { return static_cast<size_t>(batch) * kH * 2 * kM2 * kC * sizeof(float); }
 
 int fno_pack_spectral_weights(const void* w1, const void* w2, void* wk, int conj_transpose, void* stream) {
   if (!w1 || !w2 || !wk) return fail(kErrArg, "fno_pack_spectral_weights: null pointer");
@@ -112,28 +117,36 @@ int fno_mode_mix(const void* xm, const void* wk, void* ym, int batch, void* stre
   return kOk;
 }
 
-int fno_block_out(int epilogue, const void* ym, const void* act_in, const float* w0t, const float* bias,
-                  void* act_out, float* pre_out, const float* pre_in, int batch, int act_dtype, float s0, float s1,
-                  void* stream) {
-  if (!ym || !act_in || !w0t || !act_out || batch <= 0 || bad_dtype(act_dtype))
+int fno_block_out(int epilogue, const void* ym, void* z_scratch, const void* act_in, const float* w0t,
+                  const float* bias, void* act_out, float* pre_out, const float* pre_in, int batch, int act_dtype,
+                  float s0, float s1, void* stream) {
+  if (!ym || !z_scratch || !act_in || !w0t || !act_out || batch <= 0 || bad_dtype(act_dtype))
     return fail(kErrArg, "fno_block_out: bad argument");
   if (epilogue == FNO_EPI_GELU_SAVE_PRE && !pre_out) return fail(kErrArg, "fno_block_out: pre_out is null");
   if (epilogue == FNO_EPI_MUL_DGELU && !pre_in) return fail(kErrArg, "fno_block_out: pre_in is null");
-  static const bool use_cuda_cores = [] {  // A/B switch while the tensor-core kernel is being tuned (default: CUDA cores)
+  static const int impl = [] {  // A/B switch kept while the kernels are being tuned: "tc" (default), "tc1", "cuda"
     const char* v = getenv("FNO_BLOCK_OUT_IMPL");
-    return !(v != nullptr && strcmp(v, "tc") == 0);
+    if (v != nullptr && strcmp(v, "cuda") == 0) return 1;
+    if (v != nullptr && strcmp(v, "tc1") == 0) return 2;
+    return 0;
   }();
   cudaError_t e;
-  if (use_cuda_cores) {
+  if (impl == 1) {
     e = act_dtype == FNO_ACT_F32
             ? launch_block_out<float>(epilogue, ym, act_in, w0t, bias, act_out, pre_out, pre_in, batch, s0, s1, S(stream))
             : launch_block_out<__nv_bfloat16>(epilogue, ym, act_in, w0t, bias, act_out, pre_out, pre_in, batch, s0, s1,
                                               S(stream));
-  } else {
+  } else if (impl == 2) {
     e = act_dtype == FNO_ACT_F32
             ? launch_block_out_tc<float>(epilogue, ym, act_in, w0t, bias, act_out, pre_out, pre_in, batch, s0, s1, S(stream))
             : launch_block_out_tc<__nv_bfloat16>(epilogue, ym, act_in, w0t, bias, act_out, pre_out, pre_in, batch, s0,
                                                  s1, S(stream));
+  } else {
+    FNO_CUDA(launch_inv_kx(ym, z_scratch, batch, s0, s1, S(stream)), "inv_kx_kernel");
+    e = act_dtype == FNO_ACT_F32
+            ? launch_block_tc<float>(epilogue, z_scratch, act_in, w0t, bias, act_out, pre_out, pre_in, batch, S(stream))
+            : launch_block_tc<__nv_bfloat16>(epilogue, z_scratch, act_in, w0t, bias, act_out, pre_out, pre_in, batch,
+                                             S(stream));
   }
   FNO_CUDA(e, "block_out_kernel");
   return kOk;
@@ -145,7 +158,7 @@ int fno_block_fwd(const fno_weights* w, int layer, const void* act_in, void* act
   FNO_TRY(fno_spectral_dft_fwd(act_in, ws->xm, batch, act_dtype, 1.f, 1.f, stream));
   FNO_TRY(fno_mode_mix(ws->xm, w->spec_wk[layer], ws->ym, batch, stream));
   const float inv = 1.f / static_cast<float>(kHW);
-  return fno_block_out(pre_out ? FNO_EPI_GELU_SAVE_PRE : FNO_EPI_GELU, ws->ym, act_in, w->w0t[layer], w->w0_b[layer],
+  return fno_block_out(pre_out ? FNO_EPI_GELU_SAVE_PRE : FNO_EPI_GELU, ws->ym, ws->z, act_in, w->w0t[layer], w->w0_b[layer],
                        act_out, pre_out, nullptr, batch, act_dtype, inv, 2.f * inv, stream);
 }
 
@@ -173,7 +186,7 @@ int fno_project_fwd(const void* act_in, const float* mask, const fno_weights* w,
 
 int fno_forward(const fno_weights* w, const float* inputs, const float* mask, const float* case_params,
                 float* preds, const fno_workspace* ws, int batch, int act_dtype, void* stream) {
-  if (!w || !ws || !ws->act[0] || !ws->act[1] || !ws->xm || !ws->ym) return fail(kErrArg, "fno_forward: bad workspace");
+  if (!w || !ws || !ws->act[0] || !ws->act[1] || !ws->xm || !ws->ym || !ws->z) return fail(kErrArg, "fno_forward: bad workspace");
   if (w->n_layers < 1 || w->n_layers > FNO_MAX_LAYERS) return fail(kErrUnsupported, "fno_forward: n_layers out of range");
   FNO_TRY(fno_lift_fwd(inputs, mask, case_params, w, ws->act[0], batch, act_dtype, stream));
   int cur = 0;
@@ -237,7 +250,7 @@ int fno_forward_train(const fno_weights* w, const float* inputs, const float* ma
     if (!saved->act[l + 1] || !saved->pre[l] || !saved->xm[l]) return fail(kErrArg, "fno_forward_train: null saved buffer");
     FNO_TRY(fno_spectral_dft_fwd(saved->act[l], saved->xm[l], batch, act_dtype, 1.f, 1.f, stream));
     FNO_TRY(fno_mode_mix(saved->xm[l], w->spec_wk[l], ws->ym, batch, stream));
-    FNO_TRY(fno_block_out(FNO_EPI_GELU_SAVE_PRE, ws->ym, saved->act[l], w->w0t[l], w->w0_b[l], saved->act[l + 1],
+    FNO_TRY(fno_block_out(FNO_EPI_GELU_SAVE_PRE, ws->ym, ws->z, saved->act[l], w->w0t[l], w->w0_b[l], saved->act[l + 1],
                           saved->pre[l], nullptr, batch, act_dtype, inv, 2.f * inv, stream));
   }
   return fno_project_fwd(saved->act[w->n_layers], mask, w, preds, batch, act_dtype, stream);
@@ -297,7 +310,7 @@ int fno_backward(const fno_weights* w, const fno_weights_bwd* wb, const float* i
     FNO_CUDA(launch_spectral_wgrad(saved->xm[l], sc->gm, sc->gwk, batch, st), "spectral_wgrad_kernel");
     FNO_TRY(fno_unpack_spectral_grads(sc->gwk, g->spec_w1[l], g->spec_w2[l], stream));
     FNO_TRY(fno_mode_mix(sc->gm, wb->spec_wkT[l], ws->ym, batch, stream));
-    FNO_TRY(fno_block_out(l > 0 ? FNO_EPI_MUL_DGELU : FNO_EPI_PLAIN, ws->ym, dpre, wb->w0[l], nullptr, dnext, nullptr,
+    FNO_TRY(fno_block_out(l > 0 ? FNO_EPI_MUL_DGELU : FNO_EPI_PLAIN, ws->ym, ws->z, dpre, wb->w0[l], nullptr, dnext, nullptr,
                           l > 0 ? saved->pre[l - 1] : nullptr, batch, FNO_ACT_F32, 1.f, 1.f, stream));
     cur ^= 1;
   }

@@ -15,6 +15,7 @@ Codelets (N = 64 everywhere):
   rfft64_lo13        64 real in            -> bins 0..12 (complex)           forward  e^{-i..}
   cfft64_r<j>        64 complex in         -> bins {0..11, 53..63} = j mod 4  forward
   icfft64_in24_r<r>  24 complex in (bins 0..11, 52..63) -> outputs h = 8h'+r, h'=0..7   inverse
+  icfft64_in24_full  24 complex in (bins 0..11, 52..63) -> all 64 outputs               inverse
   c2r64_in12         12 complex in (bins 0..11; Im of bin 0 ignored) -> 64 real out   inverse
                      y[w] = Re sum_k Z[k] e^{+2 pi i k w/64}   (caller pre-scales Z by c_ky/HW)
 
@@ -283,6 +284,22 @@ def build_icfft64_in24_r(r):
     return g, outs
 
 
+def build_icfft64_in24_full():
+    """Inverse along kx with 24 non-zero inputs (bins 0..11, 52..63), all 64 outputs."""
+    g = Graph()
+    zero = C(None, None)
+    full = [zero] * N
+    for i, kx in enumerate(KEPT_KX):
+        full[kx] = C(g.inp(f"yre[{i}]"), g.inp(f"yim[{i}]"))
+    f = lazy_cfft(g, full, +1)
+    outs = []
+    for h in range(N):
+        v = f(h)
+        outs.append((f"ore[{h}]", v.re))
+        outs.append((f"oim[{h}]", v.im))
+    return g, outs
+
+
 def build_c2r64_in12():
     """y[w] = Re sum_{k<12} Z[k] e^{+2 pi i k w/64}, Im Z[0] ignored (C2R semantics of
     torch.fft.irfft2's last axis, reference fno2d.py:81).  Packed-pair algorithm: with
@@ -427,6 +444,10 @@ def all_codelets():
         cl.append((f"icfft64_in24_r{r}",
                    "const T* __restrict__ yre, const T* __restrict__ yim, T* __restrict__ ore, T* __restrict__ oim", o,
                    f"24 complex in (bins 0..11,52..63) -> inverse DFT outputs h=8h'+{r}, h'=0..7"))
+    g, o = build_icfft64_in24_full()
+    cl.append(("icfft64_in24_full",
+               "const T* __restrict__ yre, const T* __restrict__ yim, T* __restrict__ ore, T* __restrict__ oim", o,
+               "24 complex in (bins 0..11,52..63) -> inverse DFT, all 64 outputs"))
     g, o = build_c2r64_in12()
     cl.append(("c2r64_in12", "const T* __restrict__ zre, const T* __restrict__ zim, T* __restrict__ y", o,
                "12 complex in (Im of bin 0 ignored) -> y[w] = Re sum_k Z[k] e^{+2 pi i k w/64}, w=0..63"))
@@ -468,6 +489,11 @@ def selftest():
             v = ref[8 * hp + r]
             assert abs(res[f"ore[{hp}]"] - v.real) < 1e-12 and abs(res[f"oim[{hp}]"] - v.imag) < 1e-12
         print(f"icfft64_in24_r{r} ok", op_counts(o))
+    g, o = build_icfft64_in24_full()
+    res = evaluate(o, inp)
+    for h in range(64):
+        assert abs(res[f"ore[{h}]"] - ref[h].real) < 1e-12 and abs(res[f"oim[{h}]"] - ref[h].imag) < 1e-12
+    print("icfft64_in24_full ok", op_counts(o))
     # c2r
     zz = rng.standard_normal(12) + 1j * rng.standard_normal(12)
     g, o = build_c2r64_in12()

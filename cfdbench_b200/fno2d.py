@@ -231,10 +231,11 @@ class Fno2d(AutoCfdModel):
                 act1=torch.empty(batch, HIDDEN, H, W, dtype=adt, device=dev),
                 xm=torch.empty(batch, NMODES, HIDDEN, dtype=torch.complex64, device=dev),
                 ym=torch.empty(batch, NMODES, HIDDEN, dtype=torch.complex64, device=dev),
+                z=torch.empty(batch, H, 2 * MODES, HIDDEN, dtype=torch.float32, device=dev),
             )
             st = _lib.FnoWorkspace()
             st.act[0], st.act[1] = bufs["act0"].data_ptr(), bufs["act1"].data_ptr()
-            st.xm, st.ym = bufs["xm"].data_ptr(), bufs["ym"].data_ptr()
+            st.xm, st.ym, st.z = bufs["xm"].data_ptr(), bufs["ym"].data_ptr(), bufs["z"].data_ptr()
             ws = (st, bufs)
             if len(self._ws_cache) > 4:
                 self._ws_cache.clear()

@@ -61,6 +61,7 @@ typedef struct fno_workspace {
   void* act[2]; /* two activation buffers, B*32*4096 elements of act_dtype each (ping-pong) */
   void* xm;     /* B*288*32 complex64 */
   void* ym;     /* B*288*32 complex64 */
+  void* z;      /* B*64*24*32 float32: rows of the half-inverted spectrum, Z[b][h][2 ky + (re|im)][o] */
 } fno_workspace;
 
 int fno_version(void);
@@ -68,6 +69,7 @@ const char* fno_last_error(void);
 /* bytes of one activation buffer / one mode buffer for batch B */
 size_t fno_act_bytes(int batch, int act_dtype);
 size_t fno_modes_bytes(int batch);
+size_t fno_z_bytes(int batch);
 
 /* weights1, weights2: (32,32,12,12) complex64 as stored by the reference (fno2d.py:31-51).
  * conj_transpose=0 -> wk[k][i][o] = W[i][o][k] (forward); 1 -> wk[k][o][i] = conj(W[i][o][k]) (adjoint). */
@@ -85,10 +87,11 @@ int fno_spectral_dft_fwd(const void* act_in, void* xm, int batch, int act_dtype,
 /* (2) einsum("bixy,ioxy->boxy") on both corners (fno2d.py:54-57,73-78) */
 int fno_mode_mix(const void* xm, const void* wk, void* ym, int batch, void* stream);
 /* (3) irfft2 of the zero-padded spectrum (fno2d.py:65-72,81) + Conv2d(32,32,1) + add + GELU (fno2d.py:104-111).
- *     s0/s1 scale the ky=0 / ky>0 bins (forward: 1/4096, 2/4096).  pre_out/pre_in: see FNO_EPI_*. */
-int fno_block_out(int epilogue, const void* ym, const void* act_in, const float* w0t, const float* bias,
-                  void* act_out, float* pre_out, const float* pre_in, int batch, int act_dtype, float s0, float s1,
-                  void* stream);
+ *     s0/s1 scale the ky=0 / ky>0 bins (forward: 1/4096, 2/4096).  pre_out/pre_in: see FNO_EPI_*.
+ *     z_scratch: fno_z_bytes(batch) bytes (inverse along kx runs first, the tensor-core stage consumes it). */
+int fno_block_out(int epilogue, const void* ym, void* z_scratch, const void* act_in, const float* w0t,
+                  const float* bias, void* act_out, float* pre_out, const float* pre_in, int batch, int act_dtype,
+                  float s0, float s1, void* stream);
 /* all three: act_out = FnoBlock_l(act_in) */
 int fno_block_fwd(const fno_weights* w, int layer, const void* act_in, void* act_out, float* pre_out,
                   const fno_workspace* ws, int batch, int act_dtype, void* stream);

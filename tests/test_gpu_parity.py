@@ -132,7 +132,8 @@ def test_block_out_kernel(lib, epi):
     fwd = epi in ("gelu", "save_pre")
     s0, s1 = (1 / 4096, 2 / 4096) if fwd else (1.0, 1.0)
     xd, w0td, biasd, pred = dev(x), dev(w0.T.copy()), dev(bias), dev(pre_in)  # keep alive (async launch)
-    _lib.check(lib.fno_block_out(code, ymd.data_ptr(), xd.data_ptr(), w0td.data_ptr(),
+    zs = torch.empty(batch, 64, 24, 32, device="cuda")
+    _lib.check(lib.fno_block_out(code, ymd.data_ptr(), zs.data_ptr(), xd.data_ptr(), w0td.data_ptr(),
                                  biasd.data_ptr() if fwd else None, out.data_ptr(),
                                  pre_out.data_ptr() if epi == "save_pre" else None,
                                  pred.data_ptr() if epi == "mul_dgelu" else None, batch, _lib.ACT_F32,
@@ -187,7 +188,8 @@ def test_gelu_device_accuracy(lib):
     eye = np.eye(32, dtype=np.float32)
     out = torch.zeros(1, 32, 64, 64, device="cuda")
     xs_d, eye_d, zero_d = dev(xs), dev(eye), dev(np.zeros(32, np.float32))
-    _lib.check(lib.fno_block_out(_lib.EPI_GELU, ym.data_ptr(), xs_d.data_ptr(), eye_d.data_ptr(),
+    zs = torch.empty(1, 64, 24, 32, device="cuda")
+    _lib.check(lib.fno_block_out(_lib.EPI_GELU, ym.data_ptr(), zs.data_ptr(), xs_d.data_ptr(), eye_d.data_ptr(),
                                  zero_d.data_ptr(), out.data_ptr(), None, None, 1,
                                  _lib.ACT_F32, 1 / 4096, 2 / 4096, stream()), "block_out")
     ref = onp.gelu(xs.astype(np.float64))

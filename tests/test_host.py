@@ -41,7 +41,7 @@ def test_struct_layouts_match_header():
     from cfdbench_b200 import _lib
     P = ctypes.sizeof(ctypes.c_void_p)
     assert ctypes.sizeof(_lib.FnoWeights) == 8 + P * (2 + 3 * 8 + 4 + 2)
-    assert ctypes.sizeof(_lib.FnoWorkspace) == 4 * P
+    assert ctypes.sizeof(_lib.FnoWorkspace) == 5 * P
     assert ctypes.sizeof(_lib.FnoTrainSaved) == P * (9 + 8 + 8)
     assert ctypes.sizeof(_lib.FnoGrads) == P * (2 + 4 * 8 + 4)
     assert ctypes.sizeof(_lib.FnoBwdScratch) == 5 * P
