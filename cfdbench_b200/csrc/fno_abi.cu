@@ -1,6 +1,5 @@
 // extern "C" surface of libcfdbench_b200.so (declared in include/cfdbench_b200.h).
 #include <stdio.h>
-#include <stdlib.h>
 #include <string.h>
 
 #include "../../include/cfdbench_b200.h"
@@ -12,12 +11,6 @@ cudaError_t launch_dft_fwd(const void*, void*, int, float, float, cudaStream_t);
 cudaError_t launch_mode_mix(const void*, const void*, void*, int, cudaStream_t);
 cudaError_t launch_pack_spectral(const void*, const void*, void*, int, cudaStream_t);
 cudaError_t launch_unpack_spectral(const void*, void*, void*, cudaStream_t);
-template <typename TAct>
-cudaError_t launch_block_out(int, const void*, const void*, const float*, const float*, void*, float*, const float*,
-                             int, float, float, cudaStream_t);
-template <typename TAct>
-cudaError_t launch_block_out_tc(int, const void*, const void*, const float*, const float*, void*, float*,
-                                const float*, int, float, float, cudaStream_t);
 cudaError_t launch_inv_kx(const void*, void*, int, float, float, cudaStream_t);
 template <typename TAct>
 cudaError_t launch_block_tc(int, const void*, const void*, const float*, const float*, void*, float*, const float*, int,
@@ -25,9 +18,6 @@ cudaError_t launch_block_tc(int, const void*, const void*, const float*, const f
 template <typename TAct>
 cudaError_t launch_lift(const float*, const float*, const float*, const float*, const float*, const float*,
                         const float*, void*, int, int, cudaStream_t);
-template <typename TAct>
-cudaError_t launch_project(const void*, const float*, const float*, const float*, const float*, const float*, float*,
-                           int, cudaStream_t);
 template <typename TAct>
 cudaError_t launch_project_tc(const void*, const float*, const float*, const float*, const float*, const float*,
                               float*, int, cudaStream_t);
@@ -117,38 +107,23 @@ int fno_mode_mix(const void* xm, const void* wk, void* ym, int batch, void* stre
   return kOk;
 }
 
-int fno_block_out(int epilogue, const void* ym, void* z_scratch, const void* act_in, const float* w0t,
-                  const float* bias, void* act_out, float* pre_out, const float* pre_in, int batch, int act_dtype,
-                  float s0, float s1, void* stream) {
-  if (!ym || !z_scratch || !act_in || !w0t || !act_out || batch <= 0 || bad_dtype(act_dtype))
+int fno_spectral_inv_kx(const void* ym, void* z, int batch, float s0, float s1, void* stream) {
+  if (!ym || !z || batch <= 0) return fail(kErrArg, "fno_spectral_inv_kx: bad argument");
+  FNO_CUDA(launch_inv_kx(ym, z, batch, s0, s1, S(stream)), "inv_kx_kernel");
+  return kOk;
+}
+
+int fno_block_out(int epilogue, const void* z, const void* act_in, const float* w0t, const float* bias, void* act_out,
+                  float* pre_out, const float* pre_in, int batch, int act_dtype, void* stream) {
+  if (!z || !act_in || !w0t || !act_out || batch <= 0 || bad_dtype(act_dtype))
     return fail(kErrArg, "fno_block_out: bad argument");
   if (epilogue == FNO_EPI_GELU_SAVE_PRE && !pre_out) return fail(kErrArg, "fno_block_out: pre_out is null");
   if (epilogue == FNO_EPI_MUL_DGELU && !pre_in) return fail(kErrArg, "fno_block_out: pre_in is null");
-  static const int impl = [] {  // A/B switch kept while the kernels are being tuned: "tc" (default), "tc1", "cuda"
-    const char* v = getenv("FNO_BLOCK_OUT_IMPL");
-    if (v != nullptr && strcmp(v, "cuda") == 0) return 1;
-    if (v != nullptr && strcmp(v, "tc1") == 0) return 2;
-    return 0;
-  }();
-  cudaError_t e;
-  if (impl == 1) {
-    e = act_dtype == FNO_ACT_F32
-            ? launch_block_out<float>(epilogue, ym, act_in, w0t, bias, act_out, pre_out, pre_in, batch, s0, s1, S(stream))
-            : launch_block_out<__nv_bfloat16>(epilogue, ym, act_in, w0t, bias, act_out, pre_out, pre_in, batch, s0, s1,
-                                              S(stream));
-  } else if (impl == 2) {
-    e = act_dtype == FNO_ACT_F32
-            ? launch_block_out_tc<float>(epilogue, ym, act_in, w0t, bias, act_out, pre_out, pre_in, batch, s0, s1, S(stream))
-            : launch_block_out_tc<__nv_bfloat16>(epilogue, ym, act_in, w0t, bias, act_out, pre_out, pre_in, batch, s0,
-                                                 s1, S(stream));
-  } else {
-    FNO_CUDA(launch_inv_kx(ym, z_scratch, batch, s0, s1, S(stream)), "inv_kx_kernel");
-    e = act_dtype == FNO_ACT_F32
-            ? launch_block_tc<float>(epilogue, z_scratch, act_in, w0t, bias, act_out, pre_out, pre_in, batch, S(stream))
-            : launch_block_tc<__nv_bfloat16>(epilogue, z_scratch, act_in, w0t, bias, act_out, pre_out, pre_in, batch,
-                                             S(stream));
-  }
-  FNO_CUDA(e, "block_out_kernel");
+  cudaError_t e = act_dtype == FNO_ACT_F32
+                      ? launch_block_tc<float>(epilogue, z, act_in, w0t, bias, act_out, pre_out, pre_in, batch, S(stream))
+                      : launch_block_tc<__nv_bfloat16>(epilogue, z, act_in, w0t, bias, act_out, pre_out, pre_in, batch,
+                                                       S(stream));
+  FNO_CUDA(e, "block_tc_kernel");
   return kOk;
 }
 
@@ -158,28 +133,19 @@ int fno_block_fwd(const fno_weights* w, int layer, const void* act_in, void* act
   FNO_TRY(fno_spectral_dft_fwd(act_in, ws->xm, batch, act_dtype, 1.f, 1.f, stream));
   FNO_TRY(fno_mode_mix(ws->xm, w->spec_wk[layer], ws->ym, batch, stream));
   const float inv = 1.f / static_cast<float>(kHW);
-  return fno_block_out(pre_out ? FNO_EPI_GELU_SAVE_PRE : FNO_EPI_GELU, ws->ym, ws->z, act_in, w->w0t[layer], w->w0_b[layer],
-                       act_out, pre_out, nullptr, batch, act_dtype, inv, 2.f * inv, stream);
+  FNO_TRY(fno_spectral_inv_kx(ws->ym, ws->z, batch, inv, 2.f * inv, stream));
+  return fno_block_out(pre_out ? FNO_EPI_GELU_SAVE_PRE : FNO_EPI_GELU, ws->z, act_in, w->w0t[layer], w->w0_b[layer],
+                       act_out, pre_out, nullptr, batch, act_dtype, stream);
 }
 
 int fno_project_fwd(const void* act_in, const float* mask, const fno_weights* w, float* preds, int batch,
                     int act_dtype, void* stream) {
   if (!act_in || !mask || !w || !preds || batch <= 0 || bad_dtype(act_dtype))
     return fail(kErrArg, "fno_project_fwd: bad argument");
-  static const bool use_cuda_cores = [] {  // A/B switch while the tensor-core kernel is being validated
-    const char* v = getenv("FNO_PROJECT_IMPL");
-    return v != nullptr && strcmp(v, "cuda") == 0;
-  }();
-  cudaError_t e;
-  if (use_cuda_cores) {
-    e = act_dtype == FNO_ACT_F32
-            ? launch_project<float>(act_in, w->fc1_w, w->fc1_b, w->fc2_w, w->fc2_b, mask, preds, batch, S(stream))
-            : launch_project<__nv_bfloat16>(act_in, w->fc1_w, w->fc1_b, w->fc2_w, w->fc2_b, mask, preds, batch, S(stream));
-  } else {
-    e = act_dtype == FNO_ACT_F32
-            ? launch_project_tc<float>(act_in, w->fc1_w, w->fc1_b, w->fc2_w, w->fc2_b, mask, preds, batch, S(stream))
-            : launch_project_tc<__nv_bfloat16>(act_in, w->fc1_w, w->fc1_b, w->fc2_w, w->fc2_b, mask, preds, batch, S(stream));
-  }
+  cudaError_t e =
+      act_dtype == FNO_ACT_F32
+          ? launch_project_tc<float>(act_in, w->fc1_w, w->fc1_b, w->fc2_w, w->fc2_b, mask, preds, batch, S(stream))
+          : launch_project_tc<__nv_bfloat16>(act_in, w->fc1_w, w->fc1_b, w->fc2_w, w->fc2_b, mask, preds, batch, S(stream));
   FNO_CUDA(e, "project_kernel");
   return kOk;
 }
@@ -242,7 +208,7 @@ int fno_rollout_host(const fno_weights* w, const float* inputs_host, const float
 int fno_forward_train(const fno_weights* w, const float* inputs, const float* mask, const float* case_params,
                       float* preds, const fno_train_saved* saved, const fno_workspace* ws, int batch,
                       int act_dtype, void* stream) {
-  if (!w || !saved || !ws || !ws->ym) return fail(kErrArg, "fno_forward_train: bad argument");
+  if (!w || !saved || !ws || !ws->ym || !ws->z) return fail(kErrArg, "fno_forward_train: bad argument");
   if (w->n_layers < 1 || w->n_layers > FNO_MAX_LAYERS) return fail(kErrUnsupported, "fno_forward_train: n_layers");
   FNO_TRY(fno_lift_fwd(inputs, mask, case_params, w, saved->act[0], batch, act_dtype, stream));
   const float inv = 1.f / static_cast<float>(kHW);
@@ -250,8 +216,9 @@ int fno_forward_train(const fno_weights* w, const float* inputs, const float* ma
     if (!saved->act[l + 1] || !saved->pre[l] || !saved->xm[l]) return fail(kErrArg, "fno_forward_train: null saved buffer");
     FNO_TRY(fno_spectral_dft_fwd(saved->act[l], saved->xm[l], batch, act_dtype, 1.f, 1.f, stream));
     FNO_TRY(fno_mode_mix(saved->xm[l], w->spec_wk[l], ws->ym, batch, stream));
-    FNO_TRY(fno_block_out(FNO_EPI_GELU_SAVE_PRE, ws->ym, ws->z, saved->act[l], w->w0t[l], w->w0_b[l], saved->act[l + 1],
-                          saved->pre[l], nullptr, batch, act_dtype, inv, 2.f * inv, stream));
+    FNO_TRY(fno_spectral_inv_kx(ws->ym, ws->z, batch, inv, 2.f * inv, stream));
+    FNO_TRY(fno_block_out(FNO_EPI_GELU_SAVE_PRE, ws->z, saved->act[l], w->w0t[l], w->w0_b[l], saved->act[l + 1],
+                          saved->pre[l], nullptr, batch, act_dtype, stream));
   }
   return fno_project_fwd(saved->act[w->n_layers], mask, w, preds, batch, act_dtype, stream);
 }
@@ -262,7 +229,7 @@ int fno_backward(const fno_weights* w, const fno_weights_bwd* wb, const float* i
                  int act_dtype, void* stream) {
   if (!w || !wb || !inputs || !mask || !dpreds || !saved || !g || !sc || !ws || batch <= 0 || bad_dtype(act_dtype))
     return fail(kErrArg, "fno_backward: bad argument");
-  if (!sc->d[0] || !sc->d[1] || !sc->dz1 || !sc->gm || !sc->gwk || !ws->ym)
+  if (!sc->d[0] || !sc->d[1] || !sc->dz1 || !sc->gm || !sc->gwk || !ws->ym || !ws->z)
     return fail(kErrArg, "fno_backward: null scratch buffer");
   cudaStream_t st = S(stream);
   const int L = w->n_layers, p = w->n_case_params;
@@ -310,8 +277,9 @@ int fno_backward(const fno_weights* w, const fno_weights_bwd* wb, const float* i
     FNO_CUDA(launch_spectral_wgrad(saved->xm[l], sc->gm, sc->gwk, batch, st), "spectral_wgrad_kernel");
     FNO_TRY(fno_unpack_spectral_grads(sc->gwk, g->spec_w1[l], g->spec_w2[l], stream));
     FNO_TRY(fno_mode_mix(sc->gm, wb->spec_wkT[l], ws->ym, batch, stream));
-    FNO_TRY(fno_block_out(l > 0 ? FNO_EPI_MUL_DGELU : FNO_EPI_PLAIN, ws->ym, ws->z, dpre, wb->w0[l], nullptr, dnext, nullptr,
-                          l > 0 ? saved->pre[l - 1] : nullptr, batch, FNO_ACT_F32, 1.f, 1.f, stream));
+    FNO_TRY(fno_spectral_inv_kx(ws->ym, ws->z, batch, 1.f, 1.f, stream));
+    FNO_TRY(fno_block_out(l > 0 ? FNO_EPI_MUL_DGELU : FNO_EPI_PLAIN, ws->z, dpre, wb->w0[l], nullptr, dnext, nullptr,
+                          l > 0 ? saved->pre[l - 1] : nullptr, batch, FNO_ACT_F32, stream));
     cur ^= 1;
   }
   FNO_CUDA(launch_lift_bwd(sc->d[cur], inputs, mask, case_params, w->gx, w->gy, g->fc0_w, g->fc0_b, batch, p, st),

@@ -150,58 +150,31 @@ __device__ __forceinline__ void bt_split_store(const BtRegs<TAct>& r, float* ax_
   }
 }
 
-__device__ __forceinline__ void bt_group_barrier(int grp) {
-  asm volatile("bar.sync %0, %1;" ::"r"(grp + 1), "n"(kBtGroup) : "memory");
+template <int GRP>
+__device__ __forceinline__ void bt_group_barrier() {
+  asm volatile("bar.sync %0, %1;" ::"n"(GRP + 1), "n"(kBtGroup) : "memory");
 }
 
-template <typename TAct, int EPI>
-__global__ void __launch_bounds__(kBtThreads, 1)
-    block_tc_kernel(const float* __restrict__ z, const TAct* __restrict__ x, const float* __restrict__ w0t,
-                    const float* __restrict__ bias, const float* __restrict__ etab, TAct* __restrict__ out,
-                    float* __restrict__ pre_out, const float* __restrict__ pre_in, int n_tiles) {
-  extern __shared__ __align__(1024) unsigned char smem_raw[];  // no pointer arithmetic: keeps LDS/STS addressing
-  BtSmem& sm = *reinterpret_cast<BtSmem*>(smem_raw);
-  if ((smem_u32(smem_raw) & 127u) != 0) __trap();
+template <typename TAct, int EPI, int GRP>
+__device__ __forceinline__ void bt_pipeline(BtSmem& sm, const float* __restrict__ z, const TAct* __restrict__ x,
+                                            TAct* __restrict__ out, float* __restrict__ pre_out,
+                                            const float* __restrict__ pre_in, int n_tiles) {
   constexpr bool kBf16 = sizeof(TAct) == 2;
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int grp = warp >> 3, gtid = tid & (kBtGroup - 1), gwarp = warp & 7;
-
-  if (tid == 0) {
-#pragma unroll
-    for (int i = 0; i < 4; ++i) mbar_init(&sm.mma_bar[i >> 1][i & 1], 1);
-    fence_mbar_init();
-  }
-  if (warp == 0) tc::tmem_alloc<4 * kC>(&sm.tmem_base);
-  for (int e = tid; e < kBtM * kKE; e += kBtThreads) {
-    sm.e_hi[e] = etab[e];
-    sm.e_lo[e] = etab[kBtM * kKE + e];
-  }
-  for (int e = tid; e < kC * kKConv; e += kBtThreads) {  // B[n = o][k = i] = W0[o][i] = w0t[i][o]
-    const int i = e / kC, o = e % kC;
-    float hi, lo;
-    tc::split_tf32(w0t[e], hi, lo);
-    const uint32_t off = tc::kmajor_offset(o, i, kC) / 4;
-    sm.wb_hi[off] = hi;
-    sm.wb_lo[off] = lo;
-  }
-  if (tid < kC) sm.bias[tid] = (bias != nullptr) ? bias[tid] : 0.f;
-  tc::fence_proxy_async_smem();
-  tc::fence_before_thread_sync();
-  __syncthreads();
-  tc::fence_after_thread_sync();
-  const uint32_t tmem_base = sm.tmem_base + grp * (2 * kC);
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int gtid = tid & (kBtGroup - 1), gwarp = (tid >> 5) & 7;
+  const uint32_t tmem_base = sm.tmem_base + GRP * (2 * kC);
   constexpr uint32_t idesc = tc::make_idesc_tf32(kBtM, kC);
 
   const int first = blockIdx.x, stride = gridDim.x;
   const int n_cta = (first < n_tiles) ? (n_tiles - first + stride - 1) / stride : 0;
-  const int n_mine = (n_cta + 1 - grp) / 2;
-  auto tile_of = [&](int it) { return first + (2 * it + grp) * stride; };
+  const int n_mine = (n_cta + 1 - GRP) / 2;
+  auto tile_of = [&](int it) { return first + (2 * it + GRP) * stride; };
 
   // epilogue of local tile `it`: TMEM -> registers -> global.  Warps w and w+4 of the pipeline share TMEM lane
   // quadrant w & 3 (pixels 32(w&3)..+31 of the tile) and take output channels 0..15 / 16..31.
   auto epilogue = [&](int it) {
     const int buf = it & 1;
-    mbar_wait(&sm.mma_bar[grp][buf], (it >> 1) & 1);
+    mbar_wait(&sm.mma_bar[GRP][buf], (it >> 1) & 1);
     tc::fence_after_thread_sync();
     const int quad = gwarp & 3, half = gwarp >> 2;
     const int tile = tile_of(it);
@@ -249,11 +222,11 @@ __global__ void __launch_bounds__(kBtThreads, 1)
   for (int it = 0; it < n_mine; ++it) {
     const int buf = it & 1;
     // the single-buffered operands were last read by the MMAs of tile it-1: wait for them (normally long done)
-    if (it >= 1) mbar_wait(&sm.mma_bar[grp][(it - 1) & 1], ((it - 1) >> 1) & 1);
-    bt_split_store<TAct>(regs, sm.ax_hi[grp], sm.ax_lo[grp], sm.bz_hi[grp], sm.bz_lo[grp], gtid);
+    if (it >= 1) mbar_wait(&sm.mma_bar[GRP][(it - 1) & 1], ((it - 1) >> 1) & 1);
+    bt_split_store<TAct>(regs, sm.ax_hi[GRP], sm.ax_lo[GRP], sm.bz_hi[GRP], sm.bz_lo[GRP], gtid);
     tc::fence_proxy_async_smem();
     tc::fence_before_thread_sync();
-    bt_group_barrier(grp);
+    bt_group_barrier<GRP>();
     tc::fence_after_thread_sync();
     // prefetch AFTER the fence: the membar inside fence.proxy.async would otherwise wait for these loads
     if (it + 1 < n_mine) bt_prefetch<TAct>(regs, x, z, tile_of(it + 1), gtid);
@@ -262,8 +235,8 @@ __global__ void __launch_bounds__(kBtThreads, 1)
         // 3xTF32: pass 0 = hi*hi, pass 1 = lo*hi, pass 2 = hi*lo (A part, B part); all warp-uniform -> UR operands
         const uint32_t d_tmem = tmem_base + buf * kC;
         const uint32_t a_e[3] = {tc::smem_addr(sm.e_hi), tc::smem_addr(sm.e_lo), tc::smem_addr(sm.e_hi)};
-        const uint32_t b_z[3] = {tc::smem_addr(sm.bz_hi[grp]), tc::smem_addr(sm.bz_hi[grp]), tc::smem_addr(sm.bz_lo[grp])};
-        const uint32_t a_x[3] = {tc::smem_addr(sm.ax_hi[grp]), tc::smem_addr(sm.ax_lo[grp]), tc::smem_addr(sm.ax_hi[grp])};
+        const uint32_t b_z[3] = {tc::smem_addr(sm.bz_hi[GRP]), tc::smem_addr(sm.bz_hi[GRP]), tc::smem_addr(sm.bz_lo[GRP])};
+        const uint32_t a_x[3] = {tc::smem_addr(sm.ax_hi[GRP]), tc::smem_addr(sm.ax_lo[GRP]), tc::smem_addr(sm.ax_hi[GRP])};
         const uint32_t b_w[3] = {tc::smem_addr(sm.wb_hi), tc::smem_addr(sm.wb_hi), tc::smem_addr(sm.wb_lo)};
 #pragma unroll
         for (int pass = 0; pass < 3; ++pass) {
@@ -282,13 +255,51 @@ __global__ void __launch_bounds__(kBtThreads, 1)
           for (int ks = 0; ks < kKConv / 8; ++ks)
             tc::mma_tf32_imm<true>(d_tmem, dx0 + ((ks * 2 * kLboA) >> 4), dw0 + ((ks * 2 * kLboB) >> 4), idesc);
         }
-        tc::mma_commit(&sm.mma_bar[grp][buf]);
+        tc::mma_commit(&sm.mma_bar[GRP][buf]);
       }
       __syncwarp();
     }
     if (it >= 1) epilogue(it - 1);
   }
   if (n_mine >= 1) epilogue(n_mine - 1);
+}
+
+template <typename TAct, int EPI>
+__global__ void __launch_bounds__(kBtThreads, 1)
+    block_tc_kernel(const float* __restrict__ z, const TAct* __restrict__ x, const float* __restrict__ w0t,
+                    const float* __restrict__ bias, const float* __restrict__ etab, TAct* __restrict__ out,
+                    float* __restrict__ pre_out, const float* __restrict__ pre_in, int n_tiles) {
+  extern __shared__ __align__(1024) unsigned char smem_raw[];  // no pointer arithmetic: keeps LDS/STS addressing
+  BtSmem& sm = *reinterpret_cast<BtSmem*>(smem_raw);
+  if ((smem_u32(smem_raw) & 127u) != 0) __trap();
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const int grp = warp >> 3;
+
+  if (tid == 0) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) mbar_init(&sm.mma_bar[i >> 1][i & 1], 1);
+    fence_mbar_init();
+  }
+  if (warp == 0) tc::tmem_alloc<4 * kC>(&sm.tmem_base);
+  for (int e = tid; e < kBtM * kKE; e += kBtThreads) {
+    sm.e_hi[e] = etab[e];
+    sm.e_lo[e] = etab[kBtM * kKE + e];
+  }
+  for (int e = tid; e < kC * kKConv; e += kBtThreads) {  // B[n = o][k = i] = W0[o][i] = w0t[i][o]
+    const int i = e / kC, o = e % kC;
+    float hi, lo;
+    tc::split_tf32(w0t[e], hi, lo);
+    const uint32_t off = tc::kmajor_offset(o, i, kC) / 4;
+    sm.wb_hi[off] = hi;
+    sm.wb_lo[off] = lo;
+  }
+  if (tid < kC) sm.bias[tid] = (bias != nullptr) ? bias[tid] : 0.f;
+  tc::fence_proxy_async_smem();
+  tc::fence_before_thread_sync();
+  __syncthreads();
+  tc::fence_after_thread_sync();
+  if (grp == 0) bt_pipeline<TAct, EPI, 0>(sm, z, x, out, pre_out, pre_in, n_tiles);
+  else bt_pipeline<TAct, EPI, 1>(sm, z, x, out, pre_out, pre_in, n_tiles);
   tc::fence_before_thread_sync();
   __syncthreads();
   if (warp == 0) tc::tmem_dealloc<4 * kC>(sm.tmem_base);

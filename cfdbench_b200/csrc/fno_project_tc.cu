@@ -79,8 +79,108 @@ __device__ __forceinline__ void pt_split_store(const PtRegs<TAct>& r, float* a_h
   }
 }
 
-__device__ __forceinline__ void group_barrier(int grp) {  // named barrier of one 256-thread pipeline
-  asm volatile("bar.sync %0, %1;" ::"r"(grp + 1), "n"(kPtGroup) : "memory");
+template <int GRP>
+__device__ __forceinline__ void group_barrier() {  // named barrier of one 256-thread pipeline
+  asm volatile("bar.sync %0, %1;" ::"n"(GRP + 1), "n"(kPtGroup) : "memory");
+}
+
+template <typename TAct, int GRP>
+__device__ __forceinline__ void pt_pipeline(PtSmem& sm, const TAct* __restrict__ a, const float* __restrict__ mask,
+                                            float* __restrict__ preds, int n_tiles, float b2x, float b2y) {
+  constexpr bool kBf16 = sizeof(TAct) == 2;
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int gtid = tid & (kPtGroup - 1), gwarp = (tid >> 5) & 7;
+  const uint32_t tmem_base = sm.tmem_base + GRP * (2 * kProj);
+  constexpr uint32_t idesc = tc::make_idesc_tf32(kPtM, kProj);
+
+  // tiles of this CTA: first, first+stride, ...; pipeline g takes every other one
+  const int first = blockIdx.x, stride = gridDim.x;
+  const int n_cta = (first < n_tiles) ? (n_tiles - first + stride - 1) / stride : 0;
+  const int n_mine = (n_cta + 1 - GRP) / 2;
+  auto tile_of = [&](int it) { return first + (2 * it + GRP) * stride; };
+
+  // epilogue of local tile `it`: TMEM accumulator -> +bias -> GELU -> fc2 partial sums (two 32-column chunks)
+  auto epilogue = [&](int it) {
+    const int buf = it & 1;
+    mbar_wait(&sm.mma_bar[GRP][buf], (it >> 1) & 1);
+    tc::fence_after_thread_sync();
+    const int quad = gwarp & 3, half = gwarp >> 2;  // TMEM lane quadrant / 64-column half
+    float2 acc = make_float2(0.f, 0.f);             // (out channel 0, out channel 1)
+#pragma unroll
+    for (int chunk = 0; chunk < 2; ++chunk) {
+      float v[32];
+      const int j0 = half * 64 + chunk * 32;
+      tc::tmem_ld32(tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + buf * kProj + j0, v);
+#pragma unroll
+      for (int c = 0; c < 32; c += 2) {
+        const int j = j0 + c;
+        const float2 bb = *reinterpret_cast<const float2*>(&sm.b1[j]);
+        const float2 g = gelu_erf2(make_float2(v[c] + bb.x, v[c + 1] + bb.y));
+        const float4 wq = sm.w2q[j >> 1];
+        acc = __ffma2_rn(make_float2(g.x, g.x), make_float2(wq.x, wq.y), acc);
+        acc = __ffma2_rn(make_float2(g.y, g.y), make_float2(wq.z, wq.w), acc);
+      }
+    }
+    sm.opart[GRP][buf][half][quad * 32 + lane] = acc;  // summed in a fixed order by finalize(): deterministic
+    tc::fence_before_thread_sync();
+  };
+  // after the group barrier that follows epilogue(it): write tile `it`'s predictions
+  auto finalize = [&](int it) {
+    if (gtid < kPtM) {
+      const int buf = it & 1;
+      const int tile = tile_of(it);
+      const int b = tile / kPtTilesPerSample, pix = (tile % kPtTilesPerSample) * kPtM + gtid;
+      const float2 p0 = sm.opart[GRP][buf][0][gtid], p1 = sm.opart[GRP][buf][1][gtid];
+      const float mk = __ldg(mask + static_cast<size_t>(b) * kHW + pix);
+      preds[(static_cast<size_t>(b) * 2 + 0) * kHW + pix] = ((b2x + p0.x) + p1.x) * mk;
+      preds[(static_cast<size_t>(b) * 2 + 1) * kHW + pix] = ((b2y + p0.y) + p1.y) * mk;
+    }
+  };
+
+  PtRegs<TAct> regs;
+  if (n_mine > 0) pt_prefetch<TAct>(regs, a, tile_of(0), gtid);
+
+  for (int it = 0; it < n_mine; ++it) {
+    const int buf = it & 1;
+    // A[buf] was last read by the MMAs of tile it-2, whose completion epilogue(it-2) waited for
+    pt_split_store<TAct>(regs, sm.a_hi[GRP][buf], sm.a_lo[GRP][buf], gtid);
+    tc::fence_proxy_async_smem();
+    tc::fence_before_thread_sync();
+    group_barrier<GRP>();
+    tc::fence_after_thread_sync();
+    // prefetch AFTER the fence: the membar inside fence.proxy.async would otherwise wait for these loads
+    if (it + 1 < n_mine) pt_prefetch<TAct>(regs, a, tile_of(it + 1), gtid);
+    if (it >= 2) finalize(it - 2);
+    if (gwarp == 0) {
+      if (tc::elect_one()) {
+        const uint32_t d_tmem = tmem_base + buf * kProj;
+        const uint32_t a_s[3] = {tc::smem_addr(sm.a_hi[GRP][buf]), tc::smem_addr(sm.a_lo[GRP][buf]),
+                                 tc::smem_addr(sm.a_hi[GRP][buf])};
+        const uint32_t b_s[3] = {tc::smem_addr(sm.w_hi), tc::smem_addr(sm.w_hi), tc::smem_addr(sm.w_lo)};
+#pragma unroll
+        for (int pass = 0; pass < 3; ++pass) {
+          if (kBf16 && pass == 1) continue;
+          const uint64_t da0 = tc::make_smem_desc(a_s[pass], kPtLboA, 128);
+          const uint64_t db0 = tc::make_smem_desc(b_s[pass], kPtLboB, 128);
+#pragma unroll
+          for (int ks = 0; ks < kC / 8; ++ks) {
+            const uint64_t da = da0 + ((ks * 2 * kPtLboA) >> 4), db = db0 + ((ks * 2 * kPtLboB) >> 4);
+            if (pass == 0 && ks == 0) tc::mma_tf32_imm<false>(d_tmem, da, db, idesc);
+            else tc::mma_tf32_imm<true>(d_tmem, da, db, idesc);
+          }
+        }
+        tc::mma_commit(&sm.mma_bar[GRP][buf]);
+      }
+      __syncwarp();
+    }
+    if (it >= 1) epilogue(it - 1);
+  }
+  if (n_mine >= 1) epilogue(n_mine - 1);
+  tc::fence_before_thread_sync();
+  group_barrier<GRP>();
+  tc::fence_after_thread_sync();
+  if (n_mine >= 2) finalize(n_mine - 2);
+  if (n_mine >= 1) finalize(n_mine - 1);
 }
 
 template <typename TAct>
@@ -91,10 +191,8 @@ __global__ void __launch_bounds__(kPtThreads, 1)
   extern __shared__ __align__(1024) unsigned char smem_raw[];  // no pointer arithmetic: keeps LDS/STS addressing
   PtSmem& sm = *reinterpret_cast<PtSmem*>(smem_raw);
   if ((smem_u32(smem_raw) & 127u) != 0) __trap();
-  constexpr bool kBf16 = sizeof(TAct) == 2;
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int tid = threadIdx.x, warp = tid >> 5;
   const int grp = warp >> 3;          // pipeline 0 / 1
-  const int gtid = tid & (kPtGroup - 1), gwarp = warp & 7;
 
   if (tid == 0) {
 #pragma unroll
@@ -117,97 +215,8 @@ __global__ void __launch_bounds__(kPtThreads, 1)
   tc::fence_before_thread_sync();
   __syncthreads();
   tc::fence_after_thread_sync();
-  const uint32_t tmem_base = sm.tmem_base + grp * (2 * kProj);
-  constexpr uint32_t idesc = tc::make_idesc_tf32(kPtM, kProj);
-
-  // tiles of this CTA: first, first+stride, ...; pipeline g takes every other one
-  const int first = blockIdx.x, stride = gridDim.x;
-  const int n_cta = (first < n_tiles) ? (n_tiles - first + stride - 1) / stride : 0;
-  const int n_mine = (n_cta + 1 - grp) / 2;
-  auto tile_of = [&](int it) { return first + (2 * it + grp) * stride; };
-
-  // epilogue of local tile `it`: TMEM accumulator -> +bias -> GELU -> fc2 partial sums (two 32-column chunks)
-  auto epilogue = [&](int it) {
-    const int buf = it & 1;
-    mbar_wait(&sm.mma_bar[grp][buf], (it >> 1) & 1);
-    tc::fence_after_thread_sync();
-    const int quad = gwarp & 3, half = gwarp >> 2;  // TMEM lane quadrant / 64-column half
-    float2 acc = make_float2(0.f, 0.f);             // (out channel 0, out channel 1)
-#pragma unroll
-    for (int chunk = 0; chunk < 2; ++chunk) {
-      float v[32];
-      const int j0 = half * 64 + chunk * 32;
-      tc::tmem_ld32(tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + buf * kProj + j0, v);
-#pragma unroll
-      for (int c = 0; c < 32; c += 2) {
-        const int j = j0 + c;
-        const float2 bb = *reinterpret_cast<const float2*>(&sm.b1[j]);
-        const float2 g = gelu_erf2(make_float2(v[c] + bb.x, v[c + 1] + bb.y));
-        const float4 wq = sm.w2q[j >> 1];
-        acc = __ffma2_rn(make_float2(g.x, g.x), make_float2(wq.x, wq.y), acc);
-        acc = __ffma2_rn(make_float2(g.y, g.y), make_float2(wq.z, wq.w), acc);
-      }
-    }
-    sm.opart[grp][buf][half][quad * 32 + lane] = acc;  // summed in a fixed order by finalize(): deterministic
-    tc::fence_before_thread_sync();
-  };
-  // after the group barrier that follows epilogue(it): write tile `it`'s predictions
-  auto finalize = [&](int it) {
-    if (gtid < kPtM) {
-      const int buf = it & 1;
-      const int tile = tile_of(it);
-      const int b = tile / kPtTilesPerSample, pix = (tile % kPtTilesPerSample) * kPtM + gtid;
-      const float2 p0 = sm.opart[grp][buf][0][gtid], p1 = sm.opart[grp][buf][1][gtid];
-      const float mk = __ldg(mask + static_cast<size_t>(b) * kHW + pix);
-      preds[(static_cast<size_t>(b) * 2 + 0) * kHW + pix] = ((b2x + p0.x) + p1.x) * mk;
-      preds[(static_cast<size_t>(b) * 2 + 1) * kHW + pix] = ((b2y + p0.y) + p1.y) * mk;
-    }
-  };
-
-  PtRegs<TAct> regs;
-  if (n_mine > 0) pt_prefetch<TAct>(regs, a, tile_of(0), gtid);
-
-  for (int it = 0; it < n_mine; ++it) {
-    const int buf = it & 1;
-    // A[buf] was last read by the MMAs of tile it-2, whose completion epilogue(it-2) waited for
-    pt_split_store<TAct>(regs, sm.a_hi[grp][buf], sm.a_lo[grp][buf], gtid);
-    tc::fence_proxy_async_smem();
-    tc::fence_before_thread_sync();
-    group_barrier(grp);
-    tc::fence_after_thread_sync();
-    // prefetch AFTER the fence: the membar inside fence.proxy.async would otherwise wait for these loads
-    if (it + 1 < n_mine) pt_prefetch<TAct>(regs, a, tile_of(it + 1), gtid);
-    if (it >= 2) finalize(it - 2);
-    if (gwarp == 0) {
-      if (tc::elect_one()) {
-        const uint32_t d_tmem = tmem_base + buf * kProj;
-        const uint32_t a_s[3] = {tc::smem_addr(sm.a_hi[grp][buf]), tc::smem_addr(sm.a_lo[grp][buf]),
-                                 tc::smem_addr(sm.a_hi[grp][buf])};
-        const uint32_t b_s[3] = {tc::smem_addr(sm.w_hi), tc::smem_addr(sm.w_hi), tc::smem_addr(sm.w_lo)};
-#pragma unroll
-        for (int pass = 0; pass < 3; ++pass) {
-          if (kBf16 && pass == 1) continue;
-          const uint64_t da0 = tc::make_smem_desc(a_s[pass], kPtLboA, 128);
-          const uint64_t db0 = tc::make_smem_desc(b_s[pass], kPtLboB, 128);
-#pragma unroll
-          for (int ks = 0; ks < kC / 8; ++ks) {
-            const uint64_t da = da0 + ((ks * 2 * kPtLboA) >> 4), db = db0 + ((ks * 2 * kPtLboB) >> 4);
-            if (pass == 0 && ks == 0) tc::mma_tf32_imm<false>(d_tmem, da, db, idesc);
-            else tc::mma_tf32_imm<true>(d_tmem, da, db, idesc);
-          }
-        }
-        tc::mma_commit(&sm.mma_bar[grp][buf]);
-      }
-      __syncwarp();
-    }
-    if (it >= 1) epilogue(it - 1);
-  }
-  if (n_mine >= 1) epilogue(n_mine - 1);
-  tc::fence_before_thread_sync();
-  group_barrier(grp);
-  tc::fence_after_thread_sync();
-  if (n_mine >= 2) finalize(n_mine - 2);
-  if (n_mine >= 1) finalize(n_mine - 1);
+  if (grp == 0) pt_pipeline<TAct, 0>(sm, a, mask, preds, n_tiles, b2x, b2y);
+  else pt_pipeline<TAct, 1>(sm, a, mask, preds, n_tiles, b2x, b2y);
   tc::fence_before_thread_sync();
   __syncthreads();
   if (warp == 0) tc::tmem_dealloc<4 * kProj>(sm.tmem_base);

@@ -81,18 +81,19 @@ int fno_unpack_spectral_grads(const void* gwk, void* gw1, void* gw2, void* strea
 int fno_lift_fwd(const float* inputs, const float* mask, const float* case_params, const fno_weights* w,
                  void* act_out, int batch, int act_dtype, void* stream);
 
-/* The three phases of SpectralConv2d_fast + FnoBlock (reference fno2d.py:59-82, 106-112):            */
+/* The four phases of SpectralConv2d_fast + FnoBlock (reference fno2d.py:59-82, 106-112):            */
 /* (1) torch.fft.rfft2 restricted to the kept modes (fno2d.py:62,73-78); outputs scaled by s0 (ky=0), s1 (ky>0) */
 int fno_spectral_dft_fwd(const void* act_in, void* xm, int batch, int act_dtype, float s0, float s1, void* stream);
 /* (2) einsum("bixy,ioxy->boxy") on both corners (fno2d.py:54-57,73-78) */
 int fno_mode_mix(const void* xm, const void* wk, void* ym, int batch, void* stream);
-/* (3) irfft2 of the zero-padded spectrum (fno2d.py:65-72,81) + Conv2d(32,32,1) + add + GELU (fno2d.py:104-111).
- *     s0/s1 scale the ky=0 / ky>0 bins (forward: 1/4096, 2/4096).  pre_out/pre_in: see FNO_EPI_*.
- *     z_scratch: fno_z_bytes(batch) bytes (inverse along kx runs first, the tensor-core stage consumes it). */
-int fno_block_out(int epilogue, const void* ym, void* z_scratch, const void* act_in, const float* w0t,
-                  const float* bias, void* act_out, float* pre_out, const float* pre_in, int batch, int act_dtype,
-                  float s0, float s1, void* stream);
-/* all three: act_out = FnoBlock_l(act_in) */
+/* (3) first half of irfft2 on the zero-padded spectrum (fno2d.py:65-72,81): inverse C2C along kx of the 24 kept
+ *     rows, scaled by s0 (ky=0) / s1 (ky>0) (forward: 1/4096, 2/4096): z[b][h][2 ky + (re|im)][o], fno_z_bytes(B). */
+int fno_spectral_inv_kx(const void* ym, void* z, int batch, float s0, float s1, void* stream);
+/* (4) second half of irfft2 (C2R along ky, Im of the ky=0 column dropped) + Conv2d(32,32,1) + add + GELU
+ *     (fno2d.py:81,104-111) as one tensor-core GEMM per 128-pixel tile.  pre_out/pre_in: see FNO_EPI_*. */
+int fno_block_out(int epilogue, const void* z, const void* act_in, const float* w0t, const float* bias, void* act_out,
+                  float* pre_out, const float* pre_in, int batch, int act_dtype, void* stream);
+/* all four: act_out = FnoBlock_l(act_in) */
 int fno_block_fwd(const fno_weights* w, int layer, const void* act_in, void* act_out, float* pre_out,
                   const fno_workspace* ws, int batch, int act_dtype, void* stream);
 

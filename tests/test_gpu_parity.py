@@ -133,11 +133,18 @@ def test_block_out_kernel(lib, epi):
     s0, s1 = (1 / 4096, 2 / 4096) if fwd else (1.0, 1.0)
     xd, w0td, biasd, pred = dev(x), dev(w0.T.copy()), dev(bias), dev(pre_in)  # keep alive (async launch)
     zs = torch.empty(batch, 64, 24, 32, device="cuda")
-    _lib.check(lib.fno_block_out(code, ymd.data_ptr(), zs.data_ptr(), xd.data_ptr(), w0td.data_ptr(),
+    _lib.check(lib.fno_spectral_inv_kx(ymd.data_ptr(), zs.data_ptr(), batch, s0, s1, stream()), "inv_kx")
+    # K3a alone: Z[b][h][2ky+ri][o] = s_ky * sum_kx Y[b][o][kx][ky] e^{+2 pi i kx h/64}
+    fh = np.exp(2j * np.pi * np.outer(np.arange(64), onp.kept_rows(64, 12)) / 64)
+    zref = np.einsum("hk,bokl->bhlo", fh, ym.astype(np.complex64).astype(np.complex128)) * np.where(np.arange(12) == 0, s0, s1)[None, None, :, None]
+    zgot = zs.cpu().numpy().reshape(batch, 64, 12, 2, 32)
+    zgot = zgot[:, :, :, 0] + 1j * zgot[:, :, :, 1]
+    assert np.linalg.norm(zgot - zref) / np.linalg.norm(zref) < 2e-6
+    _lib.check(lib.fno_block_out(code, zs.data_ptr(), xd.data_ptr(), w0td.data_ptr(),
                                  biasd.data_ptr() if fwd else None, out.data_ptr(),
                                  pre_out.data_ptr() if epi == "save_pre" else None,
                                  pred.data_ptr() if epi == "mul_dgelu" else None, batch, _lib.ACT_F32,
-                                 s0, s1, stream()), "block_out")
+                                 stream()), "block_out")
     ym_r = ym.astype(np.complex64).astype(np.complex128)
     spec = onp.spectral_inverse(ym_r, 64, 64, 12, 12, c0=None if fwd else 1.0, c1=None if fwd else 1.0)
     lin = spec + np.einsum("oi,bihw->bohw", w0.astype(np.float64), x.astype(np.float64))
@@ -184,14 +191,12 @@ def test_gelu_device_accuracy(lib):
     """The erfc-polynomial GELU inside block_out: zero spectrum, identity-free path -> GELU(bias + 0)."""
     from cfdbench_b200 import _lib
     xs = np.linspace(-9, 9, 32 * 64 * 64, dtype=np.float32).reshape(1, 32, 64, 64)
-    ym = torch.zeros(1, 288, 32, dtype=torch.complex64, device="cuda")
     eye = np.eye(32, dtype=np.float32)
     out = torch.zeros(1, 32, 64, 64, device="cuda")
     xs_d, eye_d, zero_d = dev(xs), dev(eye), dev(np.zeros(32, np.float32))
-    zs = torch.empty(1, 64, 24, 32, device="cuda")
-    _lib.check(lib.fno_block_out(_lib.EPI_GELU, ym.data_ptr(), zs.data_ptr(), xs_d.data_ptr(), eye_d.data_ptr(),
-                                 zero_d.data_ptr(), out.data_ptr(), None, None, 1,
-                                 _lib.ACT_F32, 1 / 4096, 2 / 4096, stream()), "block_out")
+    zs = torch.zeros(1, 64, 24, 32, device="cuda")
+    _lib.check(lib.fno_block_out(_lib.EPI_GELU, zs.data_ptr(), xs_d.data_ptr(), eye_d.data_ptr(),
+                                 zero_d.data_ptr(), out.data_ptr(), None, None, 1, _lib.ACT_F32, stream()), "block_out")
     ref = onp.gelu(xs.astype(np.float64))
     got = out.cpu().numpy().astype(np.float64)
     assert (np.abs(got - ref) / (1 + np.abs(ref))).max() < 6e-7  # the 1x1 runs as 3xTF32 on the tensor cores
