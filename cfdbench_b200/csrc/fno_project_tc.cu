@@ -150,7 +150,10 @@ __device__ __forceinline__ void pt_pipeline(PtSmem& sm, const TAct* __restrict__
 
   for (int it = 0; it < n_mine; ++it) {
     const int buf = it & 1;
-    // A[buf] was last read by the MMAs of tile it-2, whose completion epilogue(it-2) waited for
+    // A[buf] was last read by the MMAs of tile it-2, whose completion epilogue(it-2) waited for.  Waiting for
+    // MMA(it-1) here (normally long done) also keeps a fast warp from arriving on the operand-ready barrier of
+    // tile `it` before the issuing warp has consumed the one of tile it-1 (named barriers have no phase bit).
+    if (it >= 1) mbar_wait(&sm.mma_bar[GRP][(it - 1) & 1], ((it - 1) >> 1) & 1);
     pt_split_store<TAct>(regs, sm.a_hi[GRP][buf], sm.a_lo[GRP][buf], gtid);
     tc::fence_proxy_async_smem();
     tc::fence_before_thread_sync();
