@@ -150,14 +150,8 @@ __device__ __forceinline__ void bt_split_store(const BtRegs<TAct>& r, float* ax_
   }
 }
 
-// Operand-ready handshake of one pipeline (named barrier GRP+1, 256 participants): the seven producer-only warps
-// arrive without blocking, the MMA-issuing warp syncs.  (PTX producer/consumer idiom: arrive after writing.)
 template <int GRP>
-__device__ __forceinline__ void bt_ready_arrive() {
-  asm volatile("bar.arrive %0, %1;" ::"n"(GRP + 1), "n"(kBtGroup) : "memory");
-}
-template <int GRP>
-__device__ __forceinline__ void bt_ready_sync() {
+__device__ __forceinline__ void bt_group_barrier() {
   asm volatile("bar.sync %0, %1;" ::"n"(GRP + 1), "n"(kBtGroup) : "memory");
 }
 
@@ -232,12 +226,11 @@ __device__ __forceinline__ void bt_pipeline(BtSmem& sm, const float* __restrict_
     bt_split_store<TAct>(regs, sm.ax_hi[GRP], sm.ax_lo[GRP], sm.bz_hi[GRP], sm.bz_lo[GRP], gtid);
     tc::fence_proxy_async_smem();
     tc::fence_before_thread_sync();
-    if (gwarp != 0) bt_ready_arrive<GRP>();
+    bt_group_barrier<GRP>();
+    tc::fence_after_thread_sync();
     // prefetch AFTER the fence: the membar inside fence.proxy.async would otherwise wait for these loads
     if (it + 1 < n_mine) bt_prefetch<TAct>(regs, x, z, tile_of(it + 1), gtid);
     if (gwarp == 0) {
-      bt_ready_sync<GRP>();  // all 256 threads have written (and fenced) their part of the operands
-      tc::fence_after_thread_sync();
       if (tc::elect_one()) {
         // 3xTF32: pass 0 = hi*hi, pass 1 = lo*hi, pass 2 = hi*lo (A part, B part); all warp-uniform -> UR operands
         const uint32_t d_tmem = tmem_base + buf * kC;

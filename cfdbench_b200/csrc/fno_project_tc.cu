@@ -31,7 +31,7 @@ struct PtSmem {
   alignas(128) float w_lo[kProj * kC];       // 16 KB
   alignas(16) float4 w2q[kProj / 2];         // (w2[0][j], w2[1][j], w2[0][j+1], w2[1][j+1])
   alignas(16) float b1[kProj];
-  alignas(16) float2 opart[2][2][kPtM];      // [group][buffer][pixel] fc2 partial sums of column half 0
+  alignas(16) float2 opart[2][2][2][kPtM];   // [group][buffer][column half][pixel] fc2 partial sums
   alignas(8) uint64_t mma_bar[2][2];
   uint32_t tmem_base;
 };
@@ -79,19 +79,9 @@ __device__ __forceinline__ void pt_split_store(const PtRegs<TAct>& r, float* a_h
   }
 }
 
-// Operand-ready handshake of one pipeline (named barrier GRP+1, 256 participants): the seven producer-only warps
-// arrive without blocking, the MMA-issuing warp syncs.  (PTX producer/consumer idiom: arrive after writing.)
 template <int GRP>
-__device__ __forceinline__ void ready_arrive() {
-  asm volatile("bar.arrive %0, %1;" ::"n"(GRP + 1), "n"(kPtGroup) : "memory");
-}
-template <int GRP>
-__device__ __forceinline__ void ready_sync() {
+__device__ __forceinline__ void group_barrier() {  // named barrier of one 256-thread pipeline
   asm volatile("bar.sync %0, %1;" ::"n"(GRP + 1), "n"(kPtGroup) : "memory");
-}
-// the two warps that share a TMEM lane quadrant (column halves 0 / 1) meet here to add their fc2 partial sums
-__device__ __forceinline__ void pair_sync(int id) {
-  asm volatile("bar.sync %0, 64;" ::"r"(id) : "memory");
 }
 
 template <typename TAct, int GRP>
@@ -131,17 +121,19 @@ __device__ __forceinline__ void pt_pipeline(PtSmem& sm, const TAct* __restrict__
         acc = __ffma2_rn(make_float2(g.y, g.y), make_float2(wq.z, wq.w), acc);
       }
     }
+    sm.opart[GRP][buf][half][quad * 32 + lane] = acc;  // summed in a fixed order by finalize(): deterministic
     tc::fence_before_thread_sync();
-    // half 0 publishes its partial sums, half 1 adds its own in a fixed order (deterministic) and stores
-    if (half == 0) sm.opart[GRP][buf][quad * 32 + lane] = acc;
-    pair_sync(3 + GRP * 4 + quad);
-    if (half == 1) {
-      const float2 p0 = sm.opart[GRP][buf][quad * 32 + lane];
+  };
+  // after the group barrier that follows epilogue(it): write tile `it`'s predictions
+  auto finalize = [&](int it) {
+    if (gtid < kPtM) {
+      const int buf = it & 1;
       const int tile = tile_of(it);
-      const int b = tile / kPtTilesPerSample, pix = (tile % kPtTilesPerSample) * kPtM + quad * 32 + lane;
+      const int b = tile / kPtTilesPerSample, pix = (tile % kPtTilesPerSample) * kPtM + gtid;
+      const float2 p0 = sm.opart[GRP][buf][0][gtid], p1 = sm.opart[GRP][buf][1][gtid];
       const float mk = __ldg(mask + static_cast<size_t>(b) * kHW + pix);
-      preds[(static_cast<size_t>(b) * 2 + 0) * kHW + pix] = ((b2x + p0.x) + acc.x) * mk;
-      preds[(static_cast<size_t>(b) * 2 + 1) * kHW + pix] = ((b2y + p0.y) + acc.y) * mk;
+      preds[(static_cast<size_t>(b) * 2 + 0) * kHW + pix] = ((b2x + p0.x) + p1.x) * mk;
+      preds[(static_cast<size_t>(b) * 2 + 1) * kHW + pix] = ((b2y + p0.y) + p1.y) * mk;
     }
   };
 
@@ -150,19 +142,16 @@ __device__ __forceinline__ void pt_pipeline(PtSmem& sm, const TAct* __restrict__
 
   for (int it = 0; it < n_mine; ++it) {
     const int buf = it & 1;
-    // A[buf] was last read by the MMAs of tile it-2, whose completion epilogue(it-2) waited for.  Waiting for
-    // MMA(it-1) here (normally long done) also keeps a fast warp from arriving on the operand-ready barrier of
-    // tile `it` before the issuing warp has consumed the one of tile it-1 (named barriers have no phase bit).
-    if (it >= 1) mbar_wait(&sm.mma_bar[GRP][(it - 1) & 1], ((it - 1) >> 1) & 1);
+    // A[buf] was last read by the MMAs of tile it-2, whose completion epilogue(it-2) waited for
     pt_split_store<TAct>(regs, sm.a_hi[GRP][buf], sm.a_lo[GRP][buf], gtid);
     tc::fence_proxy_async_smem();
     tc::fence_before_thread_sync();
-    if (gwarp != 0) ready_arrive<GRP>();
+    group_barrier<GRP>();
+    tc::fence_after_thread_sync();
     // prefetch AFTER the fence: the membar inside fence.proxy.async would otherwise wait for these loads
     if (it + 1 < n_mine) pt_prefetch<TAct>(regs, a, tile_of(it + 1), gtid);
+    if (it >= 2) finalize(it - 2);
     if (gwarp == 0) {
-      ready_sync<GRP>();  // all 256 threads have written (and fenced) their part of the operand
-      tc::fence_after_thread_sync();
       if (tc::elect_one()) {
         const uint32_t d_tmem = tmem_base + buf * kProj;
         const uint32_t a_s[3] = {tc::smem_addr(sm.a_hi[GRP][buf]), tc::smem_addr(sm.a_lo[GRP][buf]),
@@ -187,6 +176,11 @@ __device__ __forceinline__ void pt_pipeline(PtSmem& sm, const TAct* __restrict__
     if (it >= 1) epilogue(it - 1);
   }
   if (n_mine >= 1) epilogue(n_mine - 1);
+  tc::fence_before_thread_sync();
+  group_barrier<GRP>();
+  tc::fence_after_thread_sync();
+  if (n_mine >= 2) finalize(n_mine - 2);
+  if (n_mine >= 1) finalize(n_mine - 1);
 }
 
 template <typename TAct>
