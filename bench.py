@@ -238,7 +238,7 @@ def run_reference(args, rank: int, world: int):
     not exist on the GPU box and the reference is pure Python/PyTorch, so there is nothing to compile)."""
     if rank != 0:
         return
-    torch.set_num_threads(os.cpu_count() or 1)
+    # torch's default thread count = physical cores; using all SMT threads is 3x slower for this workload
     from oracle import fno_torch_port as opt
     p = synth.n_case_params("cavity")
     sd = synth.make_state_dict(0, n_params=p)

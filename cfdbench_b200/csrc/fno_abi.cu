@@ -9,7 +9,6 @@ namespace fno {
 template <typename TAct>
 cudaError_t launch_dft_fwd(const void*, void*, int, float, float, cudaStream_t);
 cudaError_t launch_mode_mix(const void*, const void*, void*, int, cudaStream_t);
-cudaError_t launch_mode_mix_tc(const void*, const void*, void*, int, cudaStream_t);
 cudaError_t launch_pack_spectral(const void*, const void*, void*, int, cudaStream_t);
 cudaError_t launch_unpack_spectral(const void*, void*, void*, cudaStream_t);
 cudaError_t launch_inv_kx(const void*, void*, int, float, float, cudaStream_t);
@@ -104,7 +103,7 @@ int fno_spectral_dft_fwd(const void* act_in, void* xm, int batch, int act_dtype,
 
 int fno_mode_mix(const void* xm, const void* wk, void* ym, int batch, void* stream) {
   if (!xm || !wk || !ym || batch <= 0) return fail(kErrArg, "fno_mode_mix: bad argument");
-  FNO_CUDA(launch_mode_mix_tc(xm, wk, ym, batch, S(stream)), "mode_mix_tc_kernel");
+  FNO_CUDA(launch_mode_mix(xm, wk, ym, batch, S(stream)), "mode_mix_kernel");
   return kOk;
 }
 

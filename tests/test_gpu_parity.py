@@ -342,6 +342,12 @@ def test_full_batch_properties():
         perm = torch.randperm(256, device="cuda", generator=torch.Generator(device="cuda").manual_seed(0))
         yp = m.generate(inp[perm], cp[perm], mk[perm])
         assert torch.equal(yp, y1[perm])
+    # host tensors at this size take the chunked multi-stream path (4 x fno_rollout_host): identical result
+    hseq = m.generate_many(inp.cpu(), cp.cpu(), mk.cpu(), 1)
+    assert hseq[0].device.type == "cpu" and torch.equal(hseq[0], y1.cpu())
+    hseq2 = m.generate_many(hseq[0], cp.cpu(), mk.cpu(), 1)  # feeding the returned (pinned) buffer back is safe
+    with torch.no_grad():
+        assert torch.equal(hseq2[0], m.generate(y1, cp, mk).cpu())
     idx = [0, 97, 255]
     ref = onp.fno_forward(sd, batch["inputs"][idx], batch["case_params"][idx], batch["mask"][idx])["preds"]
     assert rel(y1[idx].cpu().numpy(), ref) < TOL
