@@ -215,6 +215,34 @@ def rel_l2_vs_oracle(model, sd, batch, steps: int = 4, nsamp: int = 2):
     return out
 
 
+def timed_train_step(p: int, batch_size: int, steps: int = 5, warmup: int = 3):
+    """fwd -> loss["nmse"].backward() -> Adam.step -> zero_grad (reference src/train_auto.py:233-260) on this GPU,
+    fp32 storage, data parallel gradient all-reduce when launched under torchrun.  Secondary number, not the metric."""
+    model, _ = build_model("f32", p)
+    if torch.distributed.is_initialized():
+        model.enable_data_parallel()
+    batch = synth.make_batch(7, batch_size, "cavity")
+    tb = {k: torch.from_numpy(v).to(model.device) for k, v in batch.items()}
+    opt = torch.optim.Adam(model.parameters(), lr=1e-4)
+    ev = []
+    for i in range(warmup + steps):
+        a, z = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        out = model(**tb)
+        out["loss"]["nmse"].backward()
+        opt.step()
+        opt.zero_grad()
+        z.record()
+        if i >= warmup:
+            ev.append((a, z))
+    torch.cuda.synchronize(model.device)
+    ms = float(np.median([a.elapsed_time(z) for a, z in ev]))
+    del model
+    torch.cuda.empty_cache()
+    return {"value": 1e3 / ms, "unit": "train steps/s per GPU", "ms_per_step": ms, "batch_per_gpu": batch_size,
+            "what": "fwd + nmse.backward + torch.optim.Adam.step, fp32 storage"}
+
+
 def cpu_baseline(sd, batch, budget_s: float = 20.0, max_steps: int = 8):
     """The reference's CPU path (oracle port: same torch.fft / einsum / conv2d / gelu calls) on this host."""
     from oracle import fno_torch_port as opt
@@ -320,6 +348,7 @@ def main():
         del model
         torch.cuda.empty_cache()
 
+    train = timed_train_step(p, min(args.batch, 64))  # all ranks take part (gradient all-reduce under torchrun)
     if rank != 0:
         if torch.distributed.is_initialized():
             torch.distributed.destroy_process_group()
@@ -367,6 +396,7 @@ def main():
         "gpu_launches": args.steps * (2 + 4 * synth.DEPTH),
         "roofline": head["roofline"], "kernels": head["kernels"], "rel_l2": head["rel_l2"],
         ("fp32_storage" if other_act == "f32" else "bf16_storage"): other,
+        "train_step": train,
         "clocks": clocks,
     }
     if world == 1 and not args.no_cpu_baseline:
