@@ -146,6 +146,7 @@ class Fno2d(AutoCfdModel):
         self._dp_group = None
         self._dp_enabled = False
         self.graph_rollout = False
+        self.host_chunks = 4  # batch chunks (streams) of the host-tensor rollout path
         self._graphs: dict = {}
 
     # ------------------------------------------------------------------------------------ plumbing
@@ -440,7 +441,7 @@ class Fno2d(AutoCfdModel):
         case_params = case_params.contiguous().float()
         mask3 = mask3.contiguous().float()
         pk = self._pack()
-        n_chunks = 4 if (steps == 1 and b >= 128 and b % 4 == 0) else 1
+        n_chunks = self.host_chunks if (steps == 1 and b >= 128 and b % self.host_chunks == 0) else 1
         cb = b // n_chunks
         key = ("host_io", b, steps, n_chunks)
         ent = self._ws_cache.get(key)
