@@ -17,6 +17,7 @@
 #include "fno_common.cuh"
 #include "tc_common.cuh"
 #include <math.h>
+#include <stddef.h>
 #include <string.h>
 
 namespace fno {
@@ -78,6 +79,7 @@ struct BtSmem {
   alignas(128) float wb_lo[kC * kKConv];
   alignas(16) float bias[kC];
   alignas(8) uint64_t mma_bar[2][2];
+  alignas(8) uint64_t etab_bar;
   uint32_t tmem_base;
 };
 
@@ -278,13 +280,15 @@ __global__ void __launch_bounds__(kBtThreads, 1)
   if (tid == 0) {
 #pragma unroll
     for (int i = 0; i < 4; ++i) mbar_init(&sm.mma_bar[i >> 1][i & 1], 1);
+    mbar_init(&sm.etab_bar, 1);
     fence_mbar_init();
+    // constant E operand (hi image then lo image, 48 KB): one TMA bulk copy straight into its UMMA layout
+    constexpr uint32_t kETabBytes = kETabFloats * sizeof(float);
+    static_assert(offsetof(BtSmem, e_lo) == offsetof(BtSmem, e_hi) + kETabBytes / 2, "e_hi / e_lo must be contiguous");
+    mbar_expect_tx(&sm.etab_bar, kETabBytes);
+    bulk_g2s(sm.e_hi, etab, kETabBytes, &sm.etab_bar);
   }
   if (warp == 0) tc::tmem_alloc<4 * kC>(&sm.tmem_base);
-  for (int e = tid; e < kBtM * kKE; e += kBtThreads) {
-    sm.e_hi[e] = etab[e];
-    sm.e_lo[e] = etab[kBtM * kKE + e];
-  }
   for (int e = tid; e < kC * kKConv; e += kBtThreads) {  // B[n = o][k = i] = W0[o][i] = w0t[i][o]
     const int i = e / kC, o = e % kC;
     float hi, lo;
@@ -298,6 +302,7 @@ __global__ void __launch_bounds__(kBtThreads, 1)
   tc::fence_before_thread_sync();
   __syncthreads();
   tc::fence_after_thread_sync();
+  mbar_wait(&sm.etab_bar, 0);
   if (grp == 0) bt_pipeline<TAct, EPI, 0>(sm, z, x, out, pre_out, pre_in, n_tiles);
   else bt_pipeline<TAct, EPI, 1>(sm, z, x, out, pre_out, pre_in, n_tiles);
   tc::fence_before_thread_sync();
