@@ -26,6 +26,9 @@ import sys
 import threading
 import time
 
+# keep stdout to the single JSON line: NCCL prints its version banner / debug lines to stdout otherwise
+os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+
 import numpy as np
 import torch
 
