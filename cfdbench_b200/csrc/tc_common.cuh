@@ -133,10 +133,12 @@ __host__ __device__ constexpr uint32_t kmajor_offset(int row, int k, int rows) {
 // hi/lo split for 3xTF32.  The tensor core TRUNCATES the low 13 mantissa bits of what it reads, which
 // would bias every product; so both parts are rounded to nearest tf32 here (cvt.rna) and the hardware
 // truncation is then a no-op: hi = rna(x), lo = rna(x - hi), |x - hi - lo| <= 2^-22 |x|, unbiased.
+// Round-to-nearest (ties away from zero, like cvt.rna.tf32.f32) as two integer ops on the bit pattern: add half an
+// ulp of the 10-bit mantissa, clear the 13 low bits.  ptxas expands cvt.rna into ~5 instructions because it also
+// preserves NaN/Inf payloads; activations and weights here are finite, and Inf/NaN still map to Inf/NaN (the
+// exponent field is untouched unless the mantissa carry overflows a value within 2^-11 of FLT_MAX).
 __device__ __forceinline__ float round_tf32(float x) {
-  uint32_t r;
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
-  return __uint_as_float(r);
+  return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xffffe000u);
 }
 __device__ __forceinline__ void split_tf32(float x, float& hi, float& lo) {
   hi = round_tf32(x);
