@@ -1,6 +1,5 @@
 // extern "C" surface of libcfdbench_b200.so (declared in include/cfdbench_b200.h).
 #include <stdio.h>
-#include <stdlib.h>
 #include <string.h>
 
 #include "../../include/cfdbench_b200.h"
@@ -9,8 +8,6 @@
 namespace fno {
 template <typename TAct>
 cudaError_t launch_dft_fwd(const void*, void*, int, float, float, cudaStream_t);
-template <typename TAct>
-cudaError_t launch_dft_fwd_tc(const void*, void*, int, float, float, cudaStream_t);
 cudaError_t launch_mode_mix(const void*, const void*, void*, int, cudaStream_t);
 cudaError_t launch_pack_spectral(const void*, const void*, void*, int, cudaStream_t);
 cudaError_t launch_unpack_spectral(const void*, void*, void*, cudaStream_t);
@@ -98,17 +95,8 @@ int fno_lift_fwd(const float* inputs, const float* mask, const float* case_param
 
 int fno_spectral_dft_fwd(const void* act_in, void* xm, int batch, int act_dtype, float s0, float s1, void* stream) {
   if (!act_in || !xm || batch <= 0 || bad_dtype(act_dtype)) return fail(kErrArg, "fno_spectral_dft_fwd: bad argument");
-  static const bool use_cuda = [] {  // A/B switch while the tensor-core stage 1 is being validated
-    const char* v = getenv("FNO_DFT_IMPL");
-    return v != nullptr && strcmp(v, "cuda") == 0;
-  }();
-  cudaError_t e;
-  if (use_cuda)
-    e = act_dtype == FNO_ACT_F32 ? launch_dft_fwd<float>(act_in, xm, batch, s0, s1, S(stream))
-                                 : launch_dft_fwd<__nv_bfloat16>(act_in, xm, batch, s0, s1, S(stream));
-  else
-    e = act_dtype == FNO_ACT_F32 ? launch_dft_fwd_tc<float>(act_in, xm, batch, s0, s1, S(stream))
-                                 : launch_dft_fwd_tc<__nv_bfloat16>(act_in, xm, batch, s0, s1, S(stream));
+  cudaError_t e = act_dtype == FNO_ACT_F32 ? launch_dft_fwd<float>(act_in, xm, batch, s0, s1, S(stream))
+                                           : launch_dft_fwd<__nv_bfloat16>(act_in, xm, batch, s0, s1, S(stream));
   FNO_CUDA(e, "dft_fwd_kernel");
   return kOk;
 }
