@@ -15,8 +15,8 @@
 
 namespace fno {
 
-constexpr int kDftPlanes = 4;     // planes per CTA
-constexpr int kDftThreads = 256;  // 64 columns x 4 planes
+constexpr int kDftPlanes = 2;     // planes per CTA (small CTAs: 4-5 resident per SM hide each other's TMA wait)
+constexpr int kDftThreads = 128;  // 64 columns x 2 planes
 constexpr int kDftRows = kDftPlanes * 13;
 constexpr int kDftRowPitch = 65;  // float2 elements; +1 keeps stage-2 row gathers conflict-free
 
@@ -71,7 +71,7 @@ __device__ __forceinline__ void row_transform_and_emit(const float2* __restrict_
 }
 
 template <typename TAct>
-__global__ void __launch_bounds__(kDftThreads, 2)
+__global__ void __launch_bounds__(kDftThreads, 4)
     dft_fwd_kernel(const TAct* __restrict__ x, float2* __restrict__ xm, float s0, float s1) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   DftSmem<TAct>& sm = *reinterpret_cast<DftSmem<TAct>*>(smem_raw);
