@@ -3,8 +3,8 @@
 // replacing irfft2 + Conv2d(32,32,1) + add + GELU of the reference FnoBlock
 // (src/models/fno/fno2d.py:65-72,81,104-111).
 //
-// K3a  inv_kx_kernel   inverse DFT along kx of the 24 kept rows (codelets icfft64_in24_q<r>, one thread per
-//                      (ky, o, h mod 4)), scaled by c_ky/HW, written as Z[b][h][k][o], k = 2 ky + (re|im): 196 KB/sample.
+// K3a  inv_kx_kernel   inverse DFT along kx of the 24 kept rows (codelet icfft64_in24_full, one thread per
+//                      (ky, o)), scaled by c_ky/HW, written as Z[b][h][k][o], k = 2 ky + (re|im): 196 KB/sample.
 // K3b  block_tc_kernel per tile of 128 consecutive pixels (2 image rows) one accumulation chain of UMMAs
 //          D[128 px][32 o] = [E (+) E | X] * [Z_h ; Z_h+1 ; W0^T]      K = 24 + 24 + 32, kind::tf32, 3xTF32
 //      E[w][k] = (cos, -sin)(2 pi ky w/64) is the C2R stage of the inverse transform as a constant matrix (its
@@ -25,50 +25,34 @@ namespace fno {
 enum : int { kEpiGelu = 0, kEpiGeluSavePre = 1, kEpiMulDgelu = 2, kEpiPlain = 3 };
 
 // ------------------------------------------------------------------------------------------------ K3a
-constexpr int kIkThreads = 256;  // 8 warps = 2 ky x 4 row residues; 6 CTAs per sample
+constexpr int kIkThreads = 192;  // 6 ky x 32 o per CTA, 2 CTAs per sample
 constexpr int kZK = 2 * kM2;     // 24 real columns per row: (ky, re|im)
 
-template <int R>
-__device__ __forceinline__ void ik_codelet(const float* yre, const float* yim, float* ore, float* oim) {
-  if constexpr (R == 0) fno_codelets::icfft64_in24_q0<float>(yre, yim, ore, oim);
-  if constexpr (R == 1) fno_codelets::icfft64_in24_q1<float>(yre, yim, ore, oim);
-  if constexpr (R == 2) fno_codelets::icfft64_in24_q2<float>(yre, yim, ore, oim);
-  if constexpr (R == 3) fno_codelets::icfft64_in24_q3<float>(yre, yim, ore, oim);
-}
-
-// warp = (ky, row residue r), lane = o: 24 kept kx bins -> the 16 rows h = 4h'+r (DIF fold mod 16 + 16-point inverse).
-// Small per-thread state (16 complex outputs) keeps many warps resident; the 4 residues of a ky share their loads in L1.
 __global__ void __launch_bounds__(kIkThreads)
     inv_kx_kernel(const float2* __restrict__ ym, float* __restrict__ z, float s0, float s1) {
   const int b = blockIdx.y;
-  const int w = blockIdx.x * (kIkThreads / 32) + (threadIdx.x >> 5);
-  const int ky = w >> 2, r = w & 3;
+  const int ky = blockIdx.x * (kIkThreads / 32) + (threadIdx.x >> 5);
   const int o = threadIdx.x & 31;
   const float2* ym_b = ym + static_cast<size_t>(b) * kModes * kC;
-  float yre[kKX], yim[kKX], ore[16], oim[16];
+  float yre[kKX], yim[kKX], ore[kH], oim[kH];
 #pragma unroll
   for (int kxi = 0; kxi < kKX; ++kxi) {
     const float2 v = __ldg(ym_b + (kxi * kM2 + ky) * kC + o);
     yre[kxi] = v.x;
     yim[kxi] = v.y;
   }
-  switch (r) {
-    case 0: ik_codelet<0>(yre, yim, ore, oim); break;
-    case 1: ik_codelet<1>(yre, yim, ore, oim); break;
-    case 2: ik_codelet<2>(yre, yim, ore, oim); break;
-    default: ik_codelet<3>(yre, yim, ore, oim); break;
-  }
+  fno_codelets::icfft64_in24_full<float>(yre, yim, ore, oim);
   const float s = (ky == 0) ? s0 : s1;
-  float* zb = z + ((static_cast<size_t>(b) * kH + r) * kZK + 2 * ky) * kC + o;
+  float* zb = z + (static_cast<size_t>(b) * kH * kZK + 2 * ky) * kC + o;
 #pragma unroll
-  for (int hp = 0; hp < 16; ++hp) {
-    zb[static_cast<size_t>(4 * hp) * kZK * kC] = ore[hp] * s;
-    zb[static_cast<size_t>(4 * hp) * kZK * kC + kC] = oim[hp] * s;
+  for (int h = 0; h < kH; ++h) {
+    zb[static_cast<size_t>(h) * kZK * kC] = ore[h] * s;
+    zb[static_cast<size_t>(h) * kZK * kC + kC] = oim[h] * s;
   }
 }
 
 cudaError_t launch_inv_kx(const void* ym, void* z, int batch, float s0, float s1, cudaStream_t stream) {
-  dim3 grid(kM2 * 4 / (kIkThreads / 32), batch);
+  dim3 grid(kM2 / (kIkThreads / 32), batch);
   inv_kx_kernel<<<grid, kIkThreads, 0, stream>>>(static_cast<const float2*>(ym), static_cast<float*>(z), s0, s1);
   return cudaGetLastError();
 }

@@ -15,7 +15,6 @@ Codelets (N = 64 everywhere):
   rfft64_lo13        64 real in            -> bins 0..12 (complex)           forward  e^{-i..}
   cfft64_r<j>        64 complex in         -> bins {0..11, 53..63} = j mod 4  forward
   icfft64_in24_r<r>  24 complex in (bins 0..11, 52..63) -> outputs h = 8h'+r, h'=0..7   inverse
-  icfft64_in24_q<r>  24 complex in (bins 0..11, 52..63) -> outputs h = 4h'+r, h'=0..15  inverse
   icfft64_in24_full  24 complex in (bins 0..11, 52..63) -> all 64 outputs               inverse
   c2r64_in12         12 complex in (bins 0..11; Im of bin 0 ignored) -> 64 real out   inverse
                      y[w] = Re sum_k Z[k] e^{+2 pi i k w/64}   (caller pre-scales Z by c_ky/HW)
@@ -285,29 +284,6 @@ def build_icfft64_in24_r(r):
     return g, outs
 
 
-def build_icfft64_in24_q(r):
-    """Inverse along kx with 24 non-zero inputs, outputs h = 4h'+r (h' = 0..15): DIF fold mod 16 + 16-point inverse."""
-    g = Graph()
-    ys = {kx: C(g.inp(f"yre[{i}]"), g.inp(f"yim[{i}]")) for i, kx in enumerate(KEPT_KX)}
-    folded = []
-    for m in range(16):
-        acc = None
-        for kx in KEPT_KX:
-            if kx % 16 != m:
-                continue
-            wr, wi = twiddle(kx * r, 64, +1)
-            t = cmulc(g, ys[kx], wr, wi)
-            acc = t if acc is None else cadd(g, acc, t)
-        folded.append(acc if acc is not None else C(None, None))
-    f = lazy_cfft(g, folded, +1)
-    outs = []
-    for hp in range(16):
-        v = f(hp)
-        outs.append((f"ore[{hp}]", v.re))
-        outs.append((f"oim[{hp}]", v.im))
-    return g, outs
-
-
 def build_icfft64_in24_full():
     """Inverse along kx with 24 non-zero inputs (bins 0..11, 52..63), all 64 outputs."""
     g = Graph()
@@ -468,11 +444,6 @@ def all_codelets():
         cl.append((f"icfft64_in24_r{r}",
                    "const T* __restrict__ yre, const T* __restrict__ yim, T* __restrict__ ore, T* __restrict__ oim", o,
                    f"24 complex in (bins 0..11,52..63) -> inverse DFT outputs h=8h'+{r}, h'=0..7"))
-    for r in range(4):
-        g, o = build_icfft64_in24_q(r)
-        cl.append((f"icfft64_in24_q{r}",
-                   "const T* __restrict__ yre, const T* __restrict__ yim, T* __restrict__ ore, T* __restrict__ oim", o,
-                   f"24 complex in (bins 0..11,52..63) -> inverse DFT outputs h=4h'+{r}, h'=0..15"))
     g, o = build_icfft64_in24_full()
     cl.append(("icfft64_in24_full",
                "const T* __restrict__ yre, const T* __restrict__ yim, T* __restrict__ ore, T* __restrict__ oim", o,
@@ -518,13 +489,6 @@ def selftest():
             v = ref[8 * hp + r]
             assert abs(res[f"ore[{hp}]"] - v.real) < 1e-12 and abs(res[f"oim[{hp}]"] - v.imag) < 1e-12
         print(f"icfft64_in24_r{r} ok", op_counts(o))
-    for r in range(4):
-        g, o = build_icfft64_in24_q(r)
-        res = evaluate(o, inp)
-        for hp in range(16):
-            v = ref[4 * hp + r]
-            assert abs(res[f"ore[{hp}]"] - v.real) < 1e-12 and abs(res[f"oim[{hp}]"] - v.imag) < 1e-12
-        print(f"icfft64_in24_q{r} ok", op_counts(o))
     g, o = build_icfft64_in24_full()
     res = evaluate(o, inp)
     for h in range(64):
