@@ -15,7 +15,7 @@ namespace fno {
 constexpr int kMixWarps = 4;
 constexpr int kMixThreads = kMixWarps * 32;
 constexpr int kMixChunk = 8;        // samples staged per warp iteration
-constexpr int kMixTile = 64;        // samples per CTA (16 per warp)
+constexpr int kMixTile = 128;       // samples per CTA (32 per warp: the 8 KB weight column load is amortised)
 
 __global__ void __launch_bounds__(kMixThreads)
     mode_mix_kernel(const float2* __restrict__ xm, const float2* __restrict__ wk, float2* __restrict__ ym,
@@ -34,17 +34,23 @@ __global__ void __launch_bounds__(kMixThreads)
   const int b_begin = blockIdx.y * kMixTile + warp * per_warp;
   const int b_end = min(b_begin + per_warp, batch);
 
-  for (int b0 = b_begin; b0 < b_end; b0 += kMixChunk) {
-    const int nb = min(kMixChunk, b_end - b0);
-    // stage X[b0..b0+nb)[k][:] (256 B per sample, coalesced)
-    float2 stage[kMixChunk];
+  // software pipeline: the next chunk's rows are in flight while the current one is multiplied
+  auto load_chunk = [&](float2* st, int b0) {
 #pragma unroll
     for (int s = 0; s < kMixChunk; ++s)
-      stage[s] = (s < nb) ? __ldg(xm + (static_cast<size_t>(b0 + s) * kModes + k) * kC + lane) : make_float2(0.f, 0.f);
-    __syncwarp();
+      st[s] = (b0 + s < b_end) ? __ldg(xm + (static_cast<size_t>(b0 + s) * kModes + k) * kC + lane)
+                               : make_float2(0.f, 0.f);
+  };
+  float2 stage[kMixChunk];
+  if (b_begin < b_end) load_chunk(stage, b_begin);
+
+  for (int b0 = b_begin; b0 < b_end; b0 += kMixChunk) {
+    const int nb = min(kMixChunk, b_end - b0);
+    __syncwarp();  // previous chunk's broadcast reads are done
 #pragma unroll
     for (int s = 0; s < kMixChunk; ++s) xs[warp][s][lane] = stage[s];
     __syncwarp();
+    if (b0 + kMixChunk < b_end) load_chunk(stage, b0 + kMixChunk);
 
     // acc_a += xr * (wr, wi);  acc_b += xi * (wr, wi);  y = (a.x - b.y, a.y + b.x)
     float2 acc_a[kMixChunk], acc_b[kMixChunk];
