@@ -37,6 +37,11 @@ sys.path.insert(0, ROOT)
 
 from cfdbench_b200 import dp, synth  # noqa: E402
 
+# dram__bytes_read.sum + dram__bytes_write.sum of one block_tc_kernel launch at B=256 from the `ncu --set full`
+# capture summarised in profiles/ncu_r01_final.md (bf16 storage: 117.6 MB read + 36.7 MB written; the read side
+# includes the fp32 Z rows produced by inv_kx_kernel that are not part of the algorithmic byte count).
+NCU_TRAFFIC_BYTES = {("bf16", 256): 154292224}
+
 METRIC = "fno_rollout_steps_per_sec"
 UNIT = "steps/s"
 HW = 64 * 64
@@ -369,7 +374,7 @@ def main():
         return {
             "value": world * args.steps / r["t"], "ms_per_step": 1e3 * r["t"] / args.steps,
             "roofline": {"bound": "hbm", "kernel": "block_tc_kernel", "achieved": alg / k3 / 1e9, "peak": peak,
-                         "unit": "GB/s", "frac": alg / k3 / 1e9 / peak, "traffic": None,
+                         "unit": "GB/s", "frac": alg / k3 / 1e9 / peak, "traffic": NCU_TRAFFIC_BYTES.get((act, args.batch)),
                          "algorithmic_bytes_per_launch": alg, "peak_source": peak_src,
                          "share_of_step": r["kernels"]["block_out"]["mean_us"] * 4 / step_us,
                          "fourier_layer_frac": alg / blk / 1e9 / peak},
