@@ -26,6 +26,7 @@ cudaError_t launch_project_bwd(const void*, const float*, const float*, const fl
                                const float*, float*, float*, float*, float*, float*, int, cudaStream_t);
 template <typename TP, typename TQ, int NJ, int NI>
 cudaError_t launch_chan_outer(const void*, const void*, float*, float*, int, cudaStream_t);
+cudaError_t launch_multistep_metrics(const float*, const float*, const float*, float*, int, int, cudaStream_t);
 cudaError_t launch_spectral_wgrad(const void*, const void*, void*, int, cudaStream_t);
 cudaError_t launch_lift_bwd(const float*, const float*, const float*, const float*, const float*, const float*,
                             float*, float*, int, int, cudaStream_t);
@@ -284,6 +285,14 @@ int fno_backward(const fno_weights* w, const fno_weights_bwd* wb, const float* i
   }
   FNO_CUDA(launch_lift_bwd(sc->d[cur], inputs, mask, case_params, w->gx, w->gy, g->fc0_w, g->fc0_b, batch, p, st),
            "lift_bwd_kernel");
+  return kOk;
+}
+
+int fno_multistep_metrics(const float* preds_seq, const float* label_u, const float* mask, float* sums, int steps,
+                          int batch, void* stream) {
+  if (!preds_seq || !label_u || !mask || !sums || steps <= 0 || batch <= 0)
+    return fail(kErrArg, "fno_multistep_metrics: bad argument");
+  FNO_CUDA(launch_multistep_metrics(preds_seq, label_u, mask, sums, steps, batch, S(stream)), "multistep_metrics_kernel");
   return kOk;
 }
 

@@ -168,6 +168,12 @@ int fno_backward(const fno_weights* w, const fno_weights_bwd* wb, const float* i
                  const fno_grads* grads, const fno_bwd_scratch* scratch, const fno_workspace* ws, int batch,
                  int act_dtype, void* stream);
 
+/* Rollout evaluation on the device (reference src/test_multistep.py:73-83,153-177 get_metrics on the
+ * masked u channel, three .item() syncs per step and case there).  preds_seq [S][B][2][64][64], label_u and mask
+ * [S][B][64][64]; sums [S][B][3] = (sum (p-l)^2, sum l^2, sum |p-l|) with p, l multiplied by mask. */
+int fno_multistep_metrics(const float* preds_seq, const float* label_u, const float* mask, float* sums, int steps,
+                          int batch, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

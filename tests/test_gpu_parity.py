@@ -357,3 +357,30 @@ def test_full_batch_properties():
     with torch.no_grad():
         y = m2.generate(*(torch.from_numpy(b2[k]).cuda() for k in ("inputs", "case_params", "mask")))
     assert float((y.cpu() * (1 - torch.from_numpy(b2["mask"]))).abs().max()) == 0.0
+
+
+def test_multistep_metrics_match_reference_definition():
+    """per-step mean over cases of get_metrics(preds_u*mask, label_u*mask)
+    (reference src/test_multistep.py:73-83,153-177), one launch + one D2H here."""
+    from cfdbench_b200.metrics import multistep_metrics
+    rng = np.random.default_rng(5)
+    s_, b_ = 5, 7
+    preds = rng.standard_normal((s_, b_, 2, 64, 64)).astype(np.float32)
+    label = rng.standard_normal((s_, b_, 64, 64)).astype(np.float32)
+    mask = (rng.random((s_, b_, 64, 64)) > 0.1).astype(np.float32)
+    got = multistep_metrics(torch.from_numpy(preds).cuda(), torch.from_numpy(label).cuda(), torch.from_numpy(mask).cuda())
+    assert len(got) == s_
+    for s in range(s_):
+        per_case = []
+        for b in range(b_):
+            p = preds[s, b, 0].astype(np.float64) * mask[s, b]
+            l = label[s, b].astype(np.float64) * mask[s, b]
+            mse = np.mean((p - l) ** 2)
+            per_case.append(dict(mse=mse, nmse=mse / np.mean(l ** 2), mae=np.mean(np.abs(p - l))))
+        for k in ("mse", "nmse", "mae"):
+            ref = np.mean([d[k] for d in per_case])
+            assert abs(got[s][k] - ref) < 2e-6 * abs(ref), (s, k, got[s][k], ref)
+    # also accepts the list generate_many returns
+    got2 = multistep_metrics([torch.from_numpy(preds[i]).cuda() for i in range(s_)], torch.from_numpy(label).cuda(),
+                             torch.from_numpy(mask).cuda())
+    assert got2 == got
