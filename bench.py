@@ -337,7 +337,7 @@ def main():
     sampler = ClockSampler(local)
     for act in ([args.act] + [a for a in ("bf16", "f32") if a != args.act]):
         model, sd = build_model(act, p)
-        model.graph_rollout = args.graph
+        model.graph_rollout = bool(args.graph)
         headline = act == args.act
         if headline and rank == 0:
             sampler.start()

@@ -145,7 +145,7 @@ class Fno2d(AutoCfdModel):
         self._ws_cache: dict = {}
         self._dp_group = None
         self._dp_enabled = False
-        self.graph_rollout = False
+        self.graph_rollout = "auto"  # True / False / "auto": CUDA-graph replay of device rollouts (auto: batch <= 16)
         self.host_chunks = 4  # batch chunks (streams) of the host-tensor rollout path
         self._graphs: dict = {}
 
@@ -394,7 +394,8 @@ class Fno2d(AutoCfdModel):
         pk = self._pack()
         ws, _ = self._workspace(b)
         seq = torch.empty(steps, b, self.out_chan, H, W, dtype=torch.float32, device=self.device)
-        if not self.graph_rollout:
+        use_graph = (b <= 16) if self.graph_rollout == "auto" else bool(self.graph_rollout)
+        if not use_graph:
             _lib.check(lib.fno_rollout(C.byref(pk["struct"]), inputs.data_ptr(), mask4.data_ptr(),
                                        case_params.data_ptr(), seq.data_ptr(), steps, C.byref(ws), b,
                                        self._act_code(), self._stream()), "fno_rollout")
