@@ -314,7 +314,8 @@ def main():
     ap.add_argument("--batch", type=int, default=256, help="cases per GPU")
     ap.add_argument("--act", default="bf16", choices=["bf16", "f32"], help="headline activation storage")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--graph", action="store_true", help="replay the rollout from a CUDA graph")
+    ap.add_argument("--no-graph", action="store_true",
+                    help="launch every kernel on the stream instead of replaying the rollout from a CUDA graph")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
@@ -337,7 +338,7 @@ def main():
     sampler = ClockSampler(local)
     for act in ([args.act] + [a for a in ("bf16", "f32") if a != args.act]):
         model, sd = build_model(act, p)
-        model.graph_rollout = bool(args.graph)
+        model.graph_rollout = not args.no_graph
         headline = act == args.act
         if headline and rank == 0:
             sampler.start()
@@ -397,7 +398,7 @@ def main():
             "parallelism": f"dp{world} (independent case shards, no data-path collective)",
             "l2": "inputs larger than L2: per-step working set (2 activation buffers + modes) = "
                   f"{(2 * args.batch * 32 * HW * (2 if args.act == 'bf16' else 4) + 2 * args.batch * 288 * 32 * 8) / 1e6:.0f} MB > 126 MB",
-            "cuda_graph": bool(args.graph),
+            "cuda_graph": not args.no_graph,
         },
         "sample_steps_per_s": head["value"] * args.batch,
         "e2e": {"value": world * args.steps / te, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},

@@ -35,6 +35,8 @@ __global__ void __launch_bounds__(kIkThreads)
   const int o = threadIdx.x & 31;
   const float2* ym_b = ym + static_cast<size_t>(b) * kModes * kC;
   float yre[kKX], yim[kKX], ore[kH], oim[kH];
+  pdl_wait();
+  pdl_launch_dependents();
 #pragma unroll
   for (int kxi = 0; kxi < kKX; ++kxi) {
     const float2 v = __ldg(ym_b + (kxi * kM2 + ky) * kC + o);
@@ -53,8 +55,8 @@ __global__ void __launch_bounds__(kIkThreads)
 
 cudaError_t launch_inv_kx(const void* ym, void* z, int batch, float s0, float s1, cudaStream_t stream) {
   dim3 grid(kM2 / (kIkThreads / 32), batch);
-  inv_kx_kernel<<<grid, kIkThreads, 0, stream>>>(static_cast<const float2*>(ym), static_cast<float*>(z), s0, s1);
-  return cudaGetLastError();
+  return launch_chained<false>(inv_kx_kernel, grid, dim3(kIkThreads), 0, stream, static_cast<const float2*>(ym),
+                        static_cast<float*>(z), s0, s1);
 }
 
 // ------------------------------------------------------------------------------------------------ K3b
@@ -67,6 +69,13 @@ constexpr uint32_t kLboA = (kBtM / 8) * 128;  // 2048
 constexpr uint32_t kLboB = (kC / 8) * 128;    // 512
 constexpr int kBtTilesPerSample = kHW / kBtM;  // 32
 constexpr int kETabFloats = 2 * kBtM * kKE;
+// Operand staging is done by warps 1..7 of a pipeline only: warp 0 issues the tile's ~30 MMAs in that time, so all
+// eight warps reach the group barrier together.
+constexpr int kBtWorkers = kBtGroup - 32;
+constexpr int kBtXTasks = kBtM * (kKConv / 4);               // 1024
+constexpr int kBtZTasks = kC * (kKE / 4);                    // 384
+constexpr int kBtXReps = (kBtXTasks + kBtWorkers - 1) / kBtWorkers;  // 5
+static_assert(2 * kBtWorkers >= kBtZTasks, "two z reps must cover the tile");
 
 struct BtSmem {
   alignas(128) float e_hi[kBtM * kKE];        // A operand, E part (constant)            24,576 B
@@ -85,8 +94,8 @@ struct BtSmem {
 
 template <typename TAct>
 struct BtRegs {
-  TAct x[4][4];   // task = rep*256 + gtid -> (pixel m = task & 127, channel quad = task >> 7)
-  float z[2][4];  // task = rep*256 + gtid (< 384) -> (o = task & 31, k quad = task >> 5)
+  TAct x[kBtXReps][4];  // task = rep*224 + wtid (< 1024) -> (pixel m = task & 127, channel quad = task >> 7)
+  float z[2][4];        // task = rep*224 + wtid (< 384)  -> (o = task & 31, k quad = task >> 5)
 };
 
 __device__ __forceinline__ float bt_to_float(float v) { return v; }
@@ -96,20 +105,23 @@ __device__ __forceinline__ void bt_store(__nv_bfloat16* p, float v) { *p = __flo
 
 template <typename TAct>
 __device__ __forceinline__ void bt_prefetch(BtRegs<TAct>& r, const TAct* __restrict__ x, const float* __restrict__ z,
-                                            int tile, int gtid) {
+                                            int tile, int wtid) {
+  if (wtid < 0) return;
   const int b = tile / kBtTilesPerSample, tt = tile % kBtTilesPerSample;
 #pragma unroll
-  for (int rep = 0; rep < 4; ++rep) {
-    const int task = rep * kBtGroup + gtid;
-    const int m = task & (kBtM - 1), kq = task >> 7;
-    const TAct* src = x + (static_cast<size_t>(b) * kC + 4 * kq) * kHW + tt * kBtM + m;
+  for (int rep = 0; rep < kBtXReps; ++rep) {
+    const int task = rep * kBtWorkers + wtid;
+    if (task < kBtXTasks) {
+      const int m = task & (kBtM - 1), kq = task >> 7;
+      const TAct* src = x + (static_cast<size_t>(b) * kC + 4 * kq) * kHW + tt * kBtM + m;
 #pragma unroll
-    for (int c = 0; c < 4; ++c) r.x[rep][c] = __ldg(src + static_cast<size_t>(c) * kHW);
+      for (int c = 0; c < 4; ++c) r.x[rep][c] = __ldg(src + static_cast<size_t>(c) * kHW);
+    }
   }
 #pragma unroll
   for (int rep = 0; rep < 2; ++rep) {
-    const int task = rep * kBtGroup + gtid;
-    if (task < kC * (kKE / 4)) {
+    const int task = rep * kBtWorkers + wtid;
+    if (task < kBtZTasks) {
       const int o = task & 31, kq = task >> 5;           // kq 0..11: row j = kq / 6, column quad (kq % 6)
       const int j = kq / 6, kk0 = (kq % 6) * 4;
       const float* src = z + ((static_cast<size_t>(b) * kH + 2 * tt + j) * kZK + kk0) * kC + o;
@@ -121,26 +133,29 @@ __device__ __forceinline__ void bt_prefetch(BtRegs<TAct>& r, const TAct* __restr
 
 template <typename TAct>
 __device__ __forceinline__ void bt_split_store(const BtRegs<TAct>& r, float* ax_hi, float* ax_lo, float* bz_hi,
-                                               float* bz_lo, int gtid) {
+                                               float* bz_lo, int wtid) {
+  if (wtid < 0) return;
 #pragma unroll
-  for (int rep = 0; rep < 4; ++rep) {
-    const int task = rep * kBtGroup + gtid;
-    const int m = task & (kBtM - 1), kq = task >> 7;
-    float hi[4], lo[4];
+  for (int rep = 0; rep < kBtXReps; ++rep) {
+    const int task = rep * kBtWorkers + wtid;
+    if (task < kBtXTasks) {
+      const int m = task & (kBtM - 1), kq = task >> 7;
+      float hi[4], lo[4];
 #pragma unroll
-    for (int c = 0; c < 4; ++c) {
-      const float v = bt_to_float(r.x[rep][c]);
-      if constexpr (sizeof(TAct) == 4) tc::split_tf32(v, hi[c], lo[c]);
-      else hi[c] = v;  // bf16 is tf32-exact: no lo part
+      for (int c = 0; c < 4; ++c) {
+        const float v = bt_to_float(r.x[rep][c]);
+        if constexpr (sizeof(TAct) == 4) tc::split_tf32(v, hi[c], lo[c]);
+        else hi[c] = v;  // bf16 is tf32-exact: no lo part
+      }
+      const uint32_t off = tc::kmajor_offset(m, 4 * kq, kBtM) / 4;
+      *reinterpret_cast<float4*>(ax_hi + off) = make_float4(hi[0], hi[1], hi[2], hi[3]);
+      if constexpr (sizeof(TAct) == 4) *reinterpret_cast<float4*>(ax_lo + off) = make_float4(lo[0], lo[1], lo[2], lo[3]);
     }
-    const uint32_t off = tc::kmajor_offset(m, 4 * kq, kBtM) / 4;
-    *reinterpret_cast<float4*>(ax_hi + off) = make_float4(hi[0], hi[1], hi[2], hi[3]);
-    if constexpr (sizeof(TAct) == 4) *reinterpret_cast<float4*>(ax_lo + off) = make_float4(lo[0], lo[1], lo[2], lo[3]);
   }
 #pragma unroll
   for (int rep = 0; rep < 2; ++rep) {
-    const int task = rep * kBtGroup + gtid;
-    if (task < kC * (kKE / 4)) {
+    const int task = rep * kBtWorkers + wtid;
+    if (task < kBtZTasks) {
       const int o = task & 31, kq = task >> 5;
       float hi[4], lo[4];
 #pragma unroll
@@ -164,6 +179,7 @@ __device__ __forceinline__ void bt_pipeline(BtSmem& sm, const float* __restrict_
   constexpr bool kBf16 = sizeof(TAct) == 2;
   const int tid = threadIdx.x, lane = tid & 31;
   const int gtid = tid & (kBtGroup - 1), gwarp = (tid >> 5) & 7;
+  const int wtid = gtid - 32;  // staging worker index; negative for the MMA-issuing warp
   const uint32_t tmem_base = sm.tmem_base + GRP * (2 * kC);
   constexpr uint32_t idesc = tc::make_idesc_tf32(kBtM, kC);
 
@@ -219,19 +235,19 @@ __device__ __forceinline__ void bt_pipeline(BtSmem& sm, const float* __restrict_
   };
 
   BtRegs<TAct> regs;
-  if (n_mine > 0) bt_prefetch<TAct>(regs, x, z, tile_of(0), gtid);
+  if (n_mine > 0) bt_prefetch<TAct>(regs, x, z, tile_of(0), wtid);
 
   for (int it = 0; it < n_mine; ++it) {
     const int buf = it & 1;
     // the single-buffered operands were last read by the MMAs of tile it-1: wait for them (normally long done)
     if (it >= 1) mbar_wait(&sm.mma_bar[GRP][(it - 1) & 1], ((it - 1) >> 1) & 1);
-    bt_split_store<TAct>(regs, sm.ax_hi[GRP], sm.ax_lo[GRP], sm.bz_hi[GRP], sm.bz_lo[GRP], gtid);
+    bt_split_store<TAct>(regs, sm.ax_hi[GRP], sm.ax_lo[GRP], sm.bz_hi[GRP], sm.bz_lo[GRP], wtid);
     tc::fence_proxy_async_smem();
     tc::fence_before_thread_sync();
     bt_group_barrier<GRP>();
     tc::fence_after_thread_sync();
     // prefetch AFTER the fence: the membar inside fence.proxy.async would otherwise wait for these loads
-    if (it + 1 < n_mine) bt_prefetch<TAct>(regs, x, z, tile_of(it + 1), gtid);
+    if (it + 1 < n_mine) bt_prefetch<TAct>(regs, x, z, tile_of(it + 1), wtid);
     if (gwarp == 0) {
       if (tc::elect_one()) {
         // 3xTF32: pass 0 = hi*hi, pass 1 = lo*hi, pass 2 = hi*lo (A part, B part); all warp-uniform -> UR operands
@@ -303,6 +319,8 @@ __global__ void __launch_bounds__(kBtThreads, 1)
   __syncthreads();
   tc::fence_after_thread_sync();
   mbar_wait(&sm.etab_bar, 0);
+  pdl_wait();  // everything above touched only weights / the constant E table; z and x come from the chain
+  pdl_launch_dependents();
   if (grp == 0) bt_pipeline<TAct, EPI, 0>(sm, z, x, out, pre_out, pre_in, n_tiles);
   else bt_pipeline<TAct, EPI, 1>(sm, z, x, out, pre_out, pre_in, n_tiles);
   tc::fence_before_thread_sync();
@@ -383,9 +401,8 @@ static cudaError_t launch_one(const void* z, const void* x, const float* w0t, co
   if (e != cudaSuccess) return e;
   const int n_tiles = batch * kBtTilesPerSample;
   const int grid = n_tiles < 2 * n_sm ? (n_tiles + 1) / 2 : n_sm;
-  kern<<<grid, kBtThreads, smem, stream>>>(static_cast<const float*>(z), static_cast<const TAct*>(x), w0t, bias, etab,
-                                           static_cast<TAct*>(out), pre_out, pre_in, n_tiles);
-  return cudaGetLastError();
+  return launch_chained(kern, dim3(grid), dim3(kBtThreads), smem, stream, static_cast<const float*>(z),
+                        static_cast<const TAct*>(x), w0t, bias, etab, static_cast<TAct*>(out), pre_out, pre_in, n_tiles);
 }
 
 template <typename TAct>

@@ -67,6 +67,41 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 }
 
 // ------------------------------------------------------------------------------------------------
+// Programmatic dependent launch.  The six kernels of a rollout step form one dependency chain on one
+// stream; each is launched with cudaLaunchAttributeProgrammaticStreamSerialization so that its CTAs
+// may become resident -- and run their prologue: barrier init, TMEM allocation, weight staging --
+// while the previous kernel drains.  Rules every chained kernel follows:
+//   * pdl_wait() (griddepcontrol.wait: the previous grid has completed and its writes are visible)
+//     comes before the first access to anything a kernel of the chain writes, and every CTA executes it;
+//   * pdl_launch_dependents() is issued only AFTER pdl_wait(), so at most two kernels overlap and the
+//     next kernel's prologue may read anything written two or more launches earlier (packed weights);
+//   * the prologue before pdl_wait() reads only weights / constant tables and writes only shared memory.
+// Without the launch attribute both instructions are no-ops, so the same kernels serve the training path.
+// Measured (B200, B=256, tools/pdl_sweep.py in the round-1 history): every kernel of the step carrying the
+// attribute is SLOWER (590 us/step) than none (556 us): the triple mode_mix -> inv_kx -> block_tc launched
+// early back to back costs ~10 us per layer.  With inv_kx launched normally (kEarly = false; it has no
+// prologue to overlap anyway) the step is 544 us, so that is the configuration shipped.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+template <bool kEarly = true, typename... KArgs, typename... Args>
+inline cudaError_t launch_chained(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                                  Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = kEarly ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
+
+// ------------------------------------------------------------------------------------------------
 // Activation storage types.  Arithmetic is always fp32; TAct only selects how hidden activations
 // are stored in HBM between kernels (float = parity mode, bf16 = BASELINE.json's bf16 batches).
 // ------------------------------------------------------------------------------------------------

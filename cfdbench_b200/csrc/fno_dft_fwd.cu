@@ -85,6 +85,8 @@ __global__ void __launch_bounds__(kDftThreads, 4)
     fence_mbar_init();
   }
   __syncthreads();
+  pdl_wait();
+  pdl_launch_dependents();
   if (tid == 0) {
     constexpr uint32_t bytes = kDftPlanes * kHW * sizeof(TAct);
     mbar_expect_tx(&sm.bar, bytes);
@@ -137,8 +139,8 @@ cudaError_t launch_dft_fwd(const void* x, void* xm, int batch, float s0, float s
     configured = true;
   }
   const int n_ctas = batch * kC / kDftPlanes;
-  kern<<<n_ctas, kDftThreads, smem, stream>>>(static_cast<const TAct*>(x), static_cast<float2*>(xm), s0, s1);
-  return cudaGetLastError();
+  return launch_chained(kern, dim3(n_ctas), dim3(kDftThreads), smem, stream, static_cast<const TAct*>(x),
+                        static_cast<float2*>(xm), s0, s1);
 }
 
 template cudaError_t launch_dft_fwd<float>(const void*, void*, int, float, float, cudaStream_t);

@@ -29,6 +29,8 @@ __global__ void __launch_bounds__(kMixThreads)
   const float2* wk_k = wk + static_cast<size_t>(k) * kC * kC;
 #pragma unroll
   for (int i = 0; i < kC; ++i) w[i] = __ldg(wk_k + i * kC + lane);
+  pdl_wait();  // the weight column above is not produced by the chain; xm is
+  pdl_launch_dependents();
 
   const int per_warp = kMixTile / kMixWarps;
   const int b_begin = blockIdx.y * kMixTile + warp * per_warp;
@@ -77,9 +79,8 @@ __global__ void __launch_bounds__(kMixThreads)
 
 cudaError_t launch_mode_mix(const void* xm, const void* wk, void* ym, int batch, cudaStream_t stream) {
   dim3 grid(kModes, (batch + kMixTile - 1) / kMixTile);
-  mode_mix_kernel<<<grid, kMixThreads, 0, stream>>>(static_cast<const float2*>(xm), static_cast<const float2*>(wk),
-                                                    static_cast<float2*>(ym), batch);
-  return cudaGetLastError();
+  return launch_chained(mode_mix_kernel, grid, dim3(kMixThreads), 0, stream, static_cast<const float2*>(xm),
+                        static_cast<const float2*>(wk), static_cast<float2*>(ym), batch);
 }
 
 // ------------------------------------------------------------------------------------------------

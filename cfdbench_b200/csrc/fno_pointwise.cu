@@ -26,6 +26,8 @@ __global__ void __launch_bounds__(kLiftThreads)
   const int b = blockIdx.y;
   const int tid = threadIdx.x;
   const int nin = 5 + p;
+  pdl_wait();  // first kernel of a step: inputs are the previous step's predictions
+  pdl_launch_dependents();
   if (tid < kC) {
     float cb = bias[tid];
     for (int q = 0; q < p; ++q) cb = fmaf(w[tid * nin + 5 + q], params[b * p + q], cb);
@@ -69,8 +71,8 @@ cudaError_t launch_lift(const float* inputs, const float* mask, const float* par
                         cudaStream_t stream) {
   if (p < 0 || p > kMaxCaseParams) return cudaErrorInvalidValue;
   dim3 grid(kHW / (kLiftThreads * 4), batch);
-  lift_kernel<TAct><<<grid, kLiftThreads, 0, stream>>>(inputs, mask, params, w, bias, gx, gy, static_cast<TAct*>(out), p);
-  return cudaGetLastError();
+  return launch_chained(lift_kernel<TAct>, grid, dim3(kLiftThreads), 0, stream, inputs, mask, params, w, bias, gx, gy,
+                        static_cast<TAct*>(out), p);
 }
 template cudaError_t launch_lift<float>(const float*, const float*, const float*, const float*, const float*,
                                         const float*, const float*, void*, int, int, cudaStream_t);

@@ -215,6 +215,8 @@ __global__ void __launch_bounds__(kPtThreads, 1)
   tc::fence_before_thread_sync();
   __syncthreads();
   tc::fence_after_thread_sync();
+  pdl_wait();  // fc1 / fc2 weights above are not produced by the chain; the activations are
+  pdl_launch_dependents();
   if (grp == 0) pt_pipeline<TAct, 0>(sm, a, mask, preds, n_tiles, b2x, b2y);
   else pt_pipeline<TAct, 1>(sm, a, mask, preds, n_tiles, b2x, b2y);
   tc::fence_before_thread_sync();
@@ -240,8 +242,8 @@ cudaError_t launch_project_tc(const void* a, const float* w1, const float* b1, c
   }
   const int n_tiles = batch * kPtTilesPerSample;
   const int grid = n_tiles < n_sm ? n_tiles : n_sm;
-  kern<<<grid, kPtThreads, smem, stream>>>(static_cast<const TAct*>(a), w1, b1, w2, b2, mask, preds, n_tiles);
-  return cudaGetLastError();
+  return launch_chained(kern, dim3(grid), dim3(kPtThreads), smem, stream, static_cast<const TAct*>(a), w1, b1, w2, b2,
+                        mask, preds, n_tiles);
 }
 template cudaError_t launch_project_tc<float>(const void*, const float*, const float*, const float*, const float*,
                                               const float*, float*, int, cudaStream_t);

@@ -251,6 +251,7 @@ def test_host_rollout_and_graph_rollout_equal_device_rollout():
     g, sd, batch, p = load_case("cylinder_b2_gain200")
     m = make_model(sd, p)
     inp, cp, mk = (torch.from_numpy(batch[k]) for k in ("inputs", "case_params", "mask"))
+    m.graph_rollout = False  # every kernel launched on the stream
     dseq = m.generate_many(inp.cuda(), cp.cuda(), mk.cuda(), 4)
     hseq = m.generate_many(inp, cp, mk, 4)  # host tensors -> fno_rollout_host
     assert hseq[0].device.type == "cpu"
