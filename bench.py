@@ -122,8 +122,10 @@ def timed_rollout(model, inp, cp, mk, steps: int, warmup: int):
     while time.perf_counter() - t_spin < 0.4:  # same `steps` as the timed call: its output buffer gets cached
         model.generate_many(inp, cp, mk, steps)
         torch.cuda.synchronize(dev)
-    for _ in range(max(warmup, 0)):
-        model.generate_many(inp, cp, mk, 1)
+    # W warm-up steps, issued as whole rollouts of `steps` steps (>= W steps in total): the timed call then reuses
+    # the same captured graph and output buffer, so no capture / allocation lands inside the timed region
+    for _ in range(-(-max(warmup, 0) // steps)):
+        model.generate_many(inp, cp, mk, steps)
     torch.cuda.synchronize(dev)
     if torch.distributed.is_initialized():
         torch.distributed.barrier()

@@ -178,7 +178,7 @@ __device__ __forceinline__ void bt_pipeline(BtSmem& sm, const float* __restrict_
                                             const float* __restrict__ pre_in, int n_tiles) {
   constexpr bool kBf16 = sizeof(TAct) == 2;
   const int tid = threadIdx.x, lane = tid & 31;
-  const int gtid = tid & (kBtGroup - 1), gwarp = (tid >> 5) & 7;
+  const int gtid = tid & (kBtGroup - 1), gwarp = tc::warp_index_uniform() & 7;
   const int wtid = gtid - 32;  // staging worker index; negative for the MMA-issuing warp
   const uint32_t tmem_base = sm.tmem_base + GRP * (2 * kC);
   constexpr uint32_t idesc = tc::make_idesc_tf32(kBtM, kC);
@@ -290,7 +290,7 @@ __global__ void __launch_bounds__(kBtThreads, 1)
   extern __shared__ __align__(1024) unsigned char smem_raw[];  // no pointer arithmetic: keeps LDS/STS addressing
   BtSmem& sm = *reinterpret_cast<BtSmem*>(smem_raw);
   if ((smem_u32(smem_raw) & 127u) != 0) __trap();
-  const int tid = threadIdx.x, warp = tid >> 5;
+  const int tid = threadIdx.x, warp = tc::warp_index_uniform();
   const int grp = warp >> 3;
 
   if (tid == 0) {

@@ -89,7 +89,7 @@ __device__ __forceinline__ void pt_pipeline(PtSmem& sm, const TAct* __restrict__
                                             float* __restrict__ preds, int n_tiles, float b2x, float b2y) {
   constexpr bool kBf16 = sizeof(TAct) == 2;
   const int tid = threadIdx.x, lane = tid & 31;
-  const int gtid = tid & (kPtGroup - 1), gwarp = (tid >> 5) & 7;
+  const int gtid = tid & (kPtGroup - 1), gwarp = tc::warp_index_uniform() & 7;
   const uint32_t tmem_base = sm.tmem_base + GRP * (2 * kProj);
   constexpr uint32_t idesc = tc::make_idesc_tf32(kPtM, kProj);
 
@@ -191,7 +191,7 @@ __global__ void __launch_bounds__(kPtThreads, 1)
   extern __shared__ __align__(1024) unsigned char smem_raw[];  // no pointer arithmetic: keeps LDS/STS addressing
   PtSmem& sm = *reinterpret_cast<PtSmem*>(smem_raw);
   if ((smem_u32(smem_raw) & 127u) != 0) __trap();
-  const int tid = threadIdx.x, warp = tid >> 5;
+  const int tid = threadIdx.x, warp = tc::warp_index_uniform();
   const int grp = warp >> 3;          // pipeline 0 / 1
 
   if (tid == 0) {

@@ -59,6 +59,13 @@ __host__ __device__ constexpr uint32_t make_idesc_tf32(int m, int n) {
          | (static_cast<uint32_t>(m >> 4) << 24);  // m_dim
 }
 
+// Warp index broadcast from lane 0: tells the compiler the value is warp-uniform, so branches on it are uniform
+// branches and the code under them may use the uniform datapath (UR address math, ULDC descriptors) instead of
+// re-deriving every uniform operand with R2UR (14 % of block_tc's executed instructions before this).
+__device__ __forceinline__ int warp_index_uniform() {
+  return __shfl_sync(0xffffffffu, static_cast<int>(threadIdx.x >> 5), 0);
+}
+
 // One elected lane of a converged warp.  Code guarded by this (and fed with warp-uniform values) is compiled
 // to the uniform datapath: back-to-back UTCHMMA with UR operands instead of an R2UR + ELECT loop per MMA.
 __device__ __forceinline__ bool elect_one() {

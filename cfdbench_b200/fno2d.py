@@ -416,12 +416,18 @@ class Fno2d(AutoCfdModel):
                                            self._stream()), "fno_rollout")
             side = torch.cuda.Stream(device=self.device)
             side.wait_stream(torch.cuda.current_stream(self.device))
-            with torch.cuda.stream(side):
-                run()  # warm-up: sets kernel attributes outside capture
-            torch.cuda.current_stream(self.device).wait_stream(side)
             graph = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(graph):
-                run()
+            with torch.cuda.stream(side):
+                run()  # warm-up: sets kernel attributes / builds constant tables outside capture
+                # capture_begin/end directly: the torch.cuda.graph() context manager also runs gc.collect() and
+                # empty_cache(), which turns the caller's next allocation into a multi-millisecond cudaMalloc.
+                # Nothing is allocated during the capture (all buffers are static), so no private pool is needed.
+                graph.capture_begin(capture_error_mode="thread_local")
+                try:
+                    run()
+                finally:
+                    graph.capture_end()
+            torch.cuda.current_stream(self.device).wait_stream(side)
             ent = (graph, s_in, s_cp, s_mk, s_seq, ws_bufs, pk)  # the capture holds raw pointers into these
             while len(self._graphs) >= self.max_graphs:  # oldest capture (and its static buffers) goes first
                 self._graphs.pop(next(iter(self._graphs)))
