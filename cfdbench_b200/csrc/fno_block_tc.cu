@@ -8,10 +8,11 @@
 // K3b  block_tc_kernel per tile of 128 consecutive pixels (2 image rows) one accumulation chain of UMMAs
 //          D[128 px][32 o] = [E (+) E | X] * [Z_h ; Z_h+1 ; W0^T]      K = 24 + 24 + 32, kind::tf32, 3xTF32
 //      E[w][k] = (cos, -sin)(2 pi ky w/64) is the C2R stage of the inverse transform as a constant matrix (its
-//      ky=0 imaginary column is zero: irfft2 drops Im of the DC column), block-diagonal over the two rows.
+//      ky=0 imaginary column would be zero -- irfft2 drops Im of the DC column -- and carries the bias instead:
+//      E = 1 there, the B row = bias), block-diagonal over the two rows.
 //      Persistent CTA of two independent 256-thread pipelines; operands are prefetched into registers one tile
 //      ahead (coalesced), split into tf32 hi/lo (round-to-nearest) and written as K-major UMMA operands; the
-//      accumulator lives in TMEM (double buffered) and the epilogue (thread = pixel) adds the bias, applies the
+//      accumulator lives in TMEM (double buffered) and the epilogue (thread = pixel) applies the
 //      exact GELU (or the backward epilogues) and stores coalesced along w.
 #include "fft_codelets.cuh"
 #include "fno_common.cuh"
@@ -133,7 +134,7 @@ __device__ __forceinline__ void bt_prefetch(BtRegs<TAct>& r, const TAct* __restr
 
 template <typename TAct>
 __device__ __forceinline__ void bt_split_store(const BtRegs<TAct>& r, float* ax_hi, float* ax_lo, float* bz_hi,
-                                               float* bz_lo, int wtid) {
+                                               float* bz_lo, const float* bias_s, int wtid) {
   if (wtid < 0) return;
 #pragma unroll
   for (int rep = 0; rep < kBtXReps; ++rep) {
@@ -159,7 +160,13 @@ __device__ __forceinline__ void bt_split_store(const BtRegs<TAct>& r, float* ax_
       const int o = task & 31, kq = task >> 5;
       float hi[4], lo[4];
 #pragma unroll
-      for (int c = 0; c < 4; ++c) tc::split_tf32(r.z[rep][c], hi[c], lo[c]);
+      for (int c = 0; c < 4; ++c) {
+        float v = r.z[rep][c];
+        // K columns 1 and 25 (Im of the ky = 0 column, which the C2R stage ignores) carry the bias instead: the E
+        // table holds 1 there for the rows of the matching image row, so the MMA adds bias[o] to every pixel.
+        if (c == 1 && (kq == 0 || kq == 6)) v = bias_s[o];
+        tc::split_tf32(v, hi[c], lo[c]);
+      }
       const uint32_t off = tc::kmajor_offset(o, 4 * kq, kC) / 4;
       *reinterpret_cast<float4*>(bz_hi + off) = make_float4(hi[0], hi[1], hi[2], hi[3]);
       *reinterpret_cast<float4*>(bz_lo + off) = make_float4(lo[0], lo[1], lo[2], lo[3]);
@@ -217,9 +224,7 @@ __device__ __forceinline__ void bt_pipeline(BtSmem& sm, const float* __restrict_
     for (int c = 0; c < 16; c += 2) {
       float2 p = make_float2(v[c], v[c + 1]);
       const size_t o0 = base + static_cast<size_t>(c) * kHW, o1 = o0 + kHW;
-      if constexpr (EPI == kEpiGelu || EPI == kEpiGeluSavePre) {
-        p.x += sm.bias[half * 16 + c];
-        p.y += sm.bias[half * 16 + c + 1];
+      if constexpr (EPI == kEpiGelu || EPI == kEpiGeluSavePre) {  // the accumulator already includes the bias
         if constexpr (EPI == kEpiGeluSavePre) {
           pre_out[o0] = p.x;
           pre_out[o1] = p.y;
@@ -241,7 +246,7 @@ __device__ __forceinline__ void bt_pipeline(BtSmem& sm, const float* __restrict_
     const int buf = it & 1;
     // the single-buffered operands were last read by the MMAs of tile it-1: wait for them (normally long done)
     if (it >= 1) mbar_wait(&sm.mma_bar[GRP][(it - 1) & 1], ((it - 1) >> 1) & 1);
-    bt_split_store<TAct>(regs, sm.ax_hi[GRP], sm.ax_lo[GRP], sm.bz_hi[GRP], sm.bz_lo[GRP], wtid);
+    bt_split_store<TAct>(regs, sm.ax_hi[GRP], sm.ax_lo[GRP], sm.bz_hi[GRP], sm.bz_lo[GRP], sm.bias, wtid);
     tc::fence_proxy_async_smem();
     tc::fence_before_thread_sync();
     bt_group_barrier<GRP>();
@@ -313,7 +318,8 @@ __global__ void __launch_bounds__(kBtThreads, 1)
     sm.wb_hi[off] = hi;
     sm.wb_lo[off] = lo;
   }
-  if (tid < kC) sm.bias[tid] = (bias != nullptr) ? bias[tid] : 0.f;
+  constexpr bool kHasBias = EPI == kEpiGelu || EPI == kEpiGeluSavePre;  // the adjoint epilogues take none
+  if (tid < kC) sm.bias[tid] = (kHasBias && bias != nullptr) ? bias[tid] : 0.f;
   tc::fence_proxy_async_smem();
   tc::fence_before_thread_sync();
   __syncthreads();
@@ -330,8 +336,10 @@ __global__ void __launch_bounds__(kBtThreads, 1)
 
 // ------------------------------------------------------------------------------------------------
 // Constant A-operand image of the C2R stage: rows m = 64 j + w (j = row of the tile), columns
-// k = 24 j' + 2 ky + ri;  E = cos(2 pi ky w/64) (ri=0), -sin(2 pi ky w/64) (ri=1, zero for ky=0), zero for
-// j != j'.  Built once per device in float64, split into tf32 hi/lo (round-to-nearest), laid out K-major.
+// k = 24 j' + 2 ky + ri;  E = cos(2 pi ky w/64) (ri=0), -sin(2 pi ky w/64) (ri=1), zero for j != j'.  The
+// (ky=0, ri=1) column would be identically zero (C2R drops Im of the ky=0 column); it holds 1 instead and the
+// matching B row holds the conv bias, which folds the bias add into the MMA.
+// Built once per device in float64, split into tf32 hi/lo (round-to-nearest), laid out K-major.
 // ------------------------------------------------------------------------------------------------
 static float round_tf32_host(double v) {
   float f = static_cast<float>(v);
@@ -356,7 +364,7 @@ static cudaError_t ensure_etab(const float** out, cudaStream_t stream) {
       const int j = m >> 6, w = m & 63;
       for (int ky = 0; ky < kM2; ++ky) {
         const double ang = 2.0 * 3.14159265358979323846 * ((ky * w) % 64) / 64.0;
-        const double val[2] = {cos(ang), ky == 0 ? 0.0 : -sin(ang)};
+        const double val[2] = {cos(ang), ky == 0 ? 1.0 : -sin(ang)};  // ky = 0, ri = 1: the bias column (B row = bias)
         for (int ri = 0; ri < 2; ++ri) {
           const int k = kZK * j + 2 * ky + ri;
           const float hi = round_tf32_host(val[ri]);

@@ -5,12 +5,13 @@
 //     D[128 px][128 hidden] = A[128 px][32 ch] * W1^T         (tcgen05.mma kind::tf32, M=128, N=128, K=32)
 // run as 3xTF32 (hi*hi + lo*hi + hi*lo, round-to-nearest split) so the result stays within 1e-6 of fp32.
 // The (B,128,64,64) hidden tensor of the reference (537 MB at B=256) lives only in TMEM: the epilogue reads
-// it back (thread = pixel, 32 hidden units per warp group), adds the bias, applies the exact GELU, contracts
+// it back (thread = pixel, 32 hidden units per warp group), applies the exact GELU (the bias arrives through one
+// extra K = 8 MMA step: a constant ones column times a B block holding b1), contracts
 // with fc2 in registers; the four column groups are summed in a fixed order (deterministic results).
 //
 // Persistent CTA (512 threads) per SM.  Per tile: the activation values prefetched into registers one tile
 // ahead (coalesced 16-byte loads) are split into tf32 hi/lo and written as the K-major A operand (double
-// buffered); one elected thread issues the 12 MMAs into one of two 128-column TMEM accumulators; the epilogue
+// buffered); one elected thread issues the 14 MMAs (12 + 2 bias steps; 10 with bf16 storage) into one of two 128-column TMEM accumulators; the epilogue
 // of the previous tile overlaps them.
 #include "fno_common.cuh"
 #include "tc_common.cuh"
@@ -29,8 +30,10 @@ struct PtSmem {
   alignas(128) float a_lo[2][2][kPtM * kC];  // 4 x 16 KB
   alignas(128) float w_hi[kProj * kC];       // 16 KB   B operand: [n = hidden j][k = channel i]
   alignas(128) float w_lo[kProj * kC];       // 16 KB
+  alignas(128) float ones[kPtM * 8];         // 4 KB    A operand of the bias step: column 0 = 1, columns 1..7 = 0
+  alignas(128) float bb_hi[kProj * 8];       // 4 KB    B operand of the bias step: column 0 = b1[j] (tf32 hi / lo)
+  alignas(128) float bb_lo[kProj * 8];
   alignas(16) float4 w2q[kProj / 2];         // (w2[0][j], w2[1][j], w2[0][j+1], w2[1][j+1])
-  alignas(16) float b1[kProj];
   alignas(16) float2 opart[2][2][2][kPtM];   // [group][buffer][column half][pixel] fc2 partial sums
   alignas(8) uint64_t mma_bar[2][2];
   uint32_t tmem_base;
@@ -114,8 +117,7 @@ __device__ __forceinline__ void pt_pipeline(PtSmem& sm, const TAct* __restrict__
 #pragma unroll
       for (int c = 0; c < 32; c += 2) {
         const int j = j0 + c;
-        const float2 bb = *reinterpret_cast<const float2*>(&sm.b1[j]);
-        const float2 g = gelu_erf2(make_float2(v[c] + bb.x, v[c + 1] + bb.y));
+        const float2 g = gelu_erf2(make_float2(v[c], v[c + 1]));  // the accumulator already includes b1
         const float4 wq = sm.w2q[j >> 1];
         acc = __ffma2_rn(make_float2(g.x, g.x), make_float2(wq.x, wq.y), acc);
         acc = __ffma2_rn(make_float2(g.y, g.y), make_float2(wq.z, wq.w), acc);
@@ -168,6 +170,9 @@ __device__ __forceinline__ void pt_pipeline(PtSmem& sm, const TAct* __restrict__
             if (pass == 0 && ks == 0) tc::mma_tf32_imm<false>(d_tmem, da, db, idesc);
             else tc::mma_tf32_imm<true>(d_tmem, da, db, idesc);
           }
+          if (pass != 1)  // bias step: ones (exact in tf32, no lo part) x b1 hi (pass 0) / b1 lo (pass 2)
+            tc::mma_tf32_imm<true>(d_tmem, tc::make_smem_desc(tc::smem_addr(sm.ones), kPtLboA, 128),
+                                   tc::make_smem_desc(tc::smem_addr(pass == 0 ? sm.bb_hi : sm.bb_lo), kPtLboB, 128), idesc);
         }
         tc::mma_commit(&sm.mma_bar[GRP][buf]);
       }
@@ -209,7 +214,15 @@ __global__ void __launch_bounds__(kPtThreads, 1)
     sm.w_lo[off] = lo;
   }
   if (tid < kProj / 2) sm.w2q[tid] = make_float4(w2[2 * tid], w2[kProj + 2 * tid], w2[2 * tid + 1], w2[kProj + 2 * tid + 1]);
-  if (tid < kProj) sm.b1[tid] = b1[tid];
+  for (int e = tid; e < kPtM * 8; e += kPtThreads)  // e = flat index of the K-major [128][8] tile: k = column
+    sm.ones[tc::kmajor_offset(e >> 3, e & 7, kPtM) / 4] = (e & 7) == 0 ? 1.f : 0.f;
+  for (int e = tid; e < kProj * 8; e += kPtThreads) {
+    float hi = 0.f, lo = 0.f;
+    if ((e & 7) == 0) tc::split_tf32(b1[e >> 3], hi, lo);
+    const uint32_t off = tc::kmajor_offset(e >> 3, e & 7, kProj) / 4;
+    sm.bb_hi[off] = hi;
+    sm.bb_lo[off] = lo;
+  }
   const float b2x = b2[0], b2y = b2[1];
   tc::fence_proxy_async_smem();
   tc::fence_before_thread_sync();

@@ -220,6 +220,19 @@ def test_device_gelu_polynomial_in_float32():
     ref = np.array([0.5 * v * (1 + erf(v / np.sqrt(2))) for v in x.astype(np.float64)])
     assert np.abs(g - ref).max() < 6e-7
     assert np.sqrt(np.mean((g - ref) ** 2)) < 1.5e-7
+    # packed form used by the tensor-core epilogues: polynomial in |x| with the 1/2 folded into the exponent
+    dco = [np.float32(float(re.search(rf"#define FNO_GELU_D{i} (\S+)f", src).group(1))) for i in range(9)]
+    for k in range(9):  # D_k = C_k 2^{-k/2}, D_0 = C_0 - 1
+        want = float(coef[k]) * 2.0 ** (-k / 2) - (1.0 if k == 0 else 0.0)
+        assert abs(float(dco[k]) - want) <= 2e-7 * max(abs(want), 1e-3), (k, dco[k], want)
+    q = np.full_like(ax, dco[8])
+    for c in dco[7::-1]:
+        q = (q * ax + c).astype(np.float32)
+    assert np.all(np.diff(q[x >= 0]) < 0)  # monotone: no clamp needed
+    h = np.exp2(q.astype(np.float64)).astype(np.float32)
+    g2 = (np.maximum(x, np.float32(0)).astype(np.float64) - ax.astype(np.float64) * h).astype(np.float32)
+    assert np.abs(g2 - ref).max() < 6e-7
+    assert np.sqrt(np.mean((g2 - ref) ** 2)) < 1.5e-7
 
 
 # ----------------------------------------------------------------------------- data-parallel (gloo)
