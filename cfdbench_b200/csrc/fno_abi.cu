@@ -11,6 +11,8 @@ cudaError_t launch_dft_fwd(const void*, void*, int, float, float, cudaStream_t);
 cudaError_t launch_mode_mix(const void*, const void*, void*, int, cudaStream_t);
 cudaError_t launch_pack_spectral(const void*, const void*, void*, int, cudaStream_t);
 cudaError_t launch_unpack_spectral(const void*, void*, void*, cudaStream_t);
+cudaError_t launch_pack_mix_operand(const void*, void*, cudaStream_t);
+size_t mix_operand_bytes();
 cudaError_t launch_inv_kx(const void*, void*, int, float, float, cudaStream_t);
 template <typename TAct>
 cudaError_t launch_block_tc(int, const void*, const void*, const float*, const float*, void*, float*, const float*, int,
@@ -74,6 +76,14 @@ int fno_pack_spectral_weights(const void* w1, const void* w2, void* wk, int conj
   return kOk;
 }
 
+size_t fno_mix_operand_bytes(void) { return mix_operand_bytes(); }
+
+int fno_pack_mix_operand(const void* wk, void* wop, void* stream) {
+  if (!wk || !wop) return fail(kErrArg, "fno_pack_mix_operand: null pointer");
+  FNO_CUDA(launch_pack_mix_operand(wk, wop, S(stream)), "pack_mix_operand_kernel");
+  return kOk;
+}
+
 int fno_unpack_spectral_grads(const void* gwk, void* gw1, void* gw2, void* stream) {
   if (!gwk || !gw1 || !gw2) return fail(kErrArg, "fno_unpack_spectral_grads: null pointer");
   FNO_CUDA(launch_unpack_spectral(gwk, gw1, gw2, S(stream)), "unpack_spectral_kernel");
@@ -104,7 +114,7 @@ int fno_spectral_dft_fwd(const void* act_in, void* xm, int batch, int act_dtype,
 
 int fno_mode_mix(const void* xm, const void* wk, void* ym, int batch, void* stream) {
   if (!xm || !wk || !ym || batch <= 0) return fail(kErrArg, "fno_mode_mix: bad argument");
-  FNO_CUDA(launch_mode_mix(xm, wk, ym, batch, S(stream)), "mode_mix_kernel");
+  FNO_CUDA(launch_mode_mix(xm, wk, ym, batch, S(stream)), "mode_mix_tc_kernel");
   return kOk;
 }
 

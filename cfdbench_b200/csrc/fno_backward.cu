@@ -289,7 +289,7 @@ template cudaError_t launch_chan_outer<float, float, 32, 32>(const void*, const 
 template cudaError_t launch_chan_outer<float, __nv_bfloat16, 32, 32>(const void*, const void*, float*, float*, int, cudaStream_t);
 
 // --------------------------------------------------------------------------------- spectral wgrad
-// gWk[k][i][o] = sum_b conj(X[b][k][i]) * G[b][k][o];  one CTA per mode k, lane = o, warps split the batch.
+// gWk[k][i][o] = sum_b conj(X[k][b][i]) * G[k][b][o];  one CTA per mode k, lane = o, warps split the batch.
 constexpr int kSwWarps = 4;
 
 __global__ void __launch_bounds__(kSwWarps * 32)
@@ -302,7 +302,7 @@ __global__ void __launch_bounds__(kSwWarps * 32)
 #pragma unroll
   for (int i = 0; i < kC; ++i) acc_a[i] = acc_b[i] = make_float2(0.f, 0.f);
   for (int b = warp; b < batch; b += kSwWarps) {
-    const size_t off = (static_cast<size_t>(b) * kModes + k) * kC + lane;
+    const size_t off = (static_cast<size_t>(k) * batch + b) * kC + lane;
     const float2 xv = __ldg(xm + off);
     const float2 g = __ldg(gm + off);
     __syncwarp();

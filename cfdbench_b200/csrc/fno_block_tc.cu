@@ -34,13 +34,14 @@ __global__ void __launch_bounds__(kIkThreads)
   const int b = blockIdx.y;
   const int ky = blockIdx.x * (kIkThreads / 32) + (threadIdx.x >> 5);
   const int o = threadIdx.x & 31;
-  const float2* ym_b = ym + static_cast<size_t>(b) * kModes * kC;
+  const float2* ym_b = ym + static_cast<size_t>(b) * kC;             // modes are stored mode-major: ym[k][b][o]
+  const size_t mode_stride = static_cast<size_t>(gridDim.y) * kC;   // batch * 32
   float yre[kKX], yim[kKX], ore[kH], oim[kH];
   pdl_wait();
   pdl_launch_dependents();
 #pragma unroll
   for (int kxi = 0; kxi < kKX; ++kxi) {
-    const float2 v = __ldg(ym_b + (kxi * kM2 + ky) * kC + o);
+    const float2 v = __ldg(ym_b + (kxi * kM2 + ky) * mode_stride + o);
     yre[kxi] = v.x;
     yim[kxi] = v.y;
   }

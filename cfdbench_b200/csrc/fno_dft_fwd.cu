@@ -39,6 +39,7 @@ __host__ __device__ constexpr int fwd_bin(int e) {
 
 template <int J>
 __device__ __forceinline__ void row_transform_and_emit(const float2* __restrict__ row, float2* __restrict__ xm_b,
+                                                       size_t mode_stride,
                                                        int kxp, int c, float s0, float s1) {
   float xre[64], xim[64], ore[6], oim[6];
 #pragma unroll
@@ -57,14 +58,14 @@ __device__ __forceinline__ void row_transform_and_emit(const float2* __restrict_
     if (q <= 11) {  // X[kx', q] = F[kx'][q], rows 0..11 (weights1 block)
       if (kxp <= 11) {
         const float s = (q == 0) ? s0 : s1;
-        xm_b[(kxp * kM2 + q) * kC + c] = make_float2(ore[e] * s, oim[e] * s);
+        xm_b[(kxp * kM2 + q) * mode_stride + c] = make_float2(ore[e] * s, oim[e] * s);
       }
     }
     const int qq = (64 - q) & 63;
     if (qq <= 11) {  // X[64-kx', qq] = conj(F[kx'][-qq]), rows 52..63 (weights2 block)
       if (kxp >= 1) {
         const float s = (qq == 0) ? s0 : s1;
-        xm_b[((kKX - kxp) * kM2 + qq) * kC + c] = make_float2(ore[e] * s, -oim[e] * s);
+        xm_b[((kKX - kxp) * kM2 + qq) * mode_stride + c] = make_float2(ore[e] * s, -oim[e] * s);
       }
     }
   }
@@ -116,13 +117,15 @@ __global__ void __launch_bounds__(kDftThreads, 4)
     if (lane < 26) {
       const int p = rho / 13, kxp = rho % 13;
       const float2* row = sm.as + rho * kDftRowPitch;
-      float2* xm_b = xm + static_cast<size_t>(b) * kModes * kC;
+      // modes are stored mode-major, xm[k][b][c]: the mix reads one mode of a whole sample tile as one contiguous block
+      const size_t mode_stride = static_cast<size_t>(gridDim.x) * kDftPlanes;  // = batch * kC float2 per mode
+      float2* xm_b = xm + static_cast<size_t>(b) * kC;
       const int c = c0 + p;
       switch (j) {
-        case 0: row_transform_and_emit<0>(row, xm_b, kxp, c, s0, s1); break;
-        case 1: row_transform_and_emit<1>(row, xm_b, kxp, c, s0, s1); break;
-        case 2: row_transform_and_emit<2>(row, xm_b, kxp, c, s0, s1); break;
-        default: row_transform_and_emit<3>(row, xm_b, kxp, c, s0, s1); break;
+        case 0: row_transform_and_emit<0>(row, xm_b, mode_stride, kxp, c, s0, s1); break;
+        case 1: row_transform_and_emit<1>(row, xm_b, mode_stride, kxp, c, s0, s1); break;
+        case 2: row_transform_and_emit<2>(row, xm_b, mode_stride, kxp, c, s0, s1); break;
+        default: row_transform_and_emit<3>(row, xm_b, mode_stride, kxp, c, s0, s1); break;
       }
     }
   }

@@ -1,87 +1,275 @@
-// K2 -- per-mode complex channel mix: Y[b][k][o] = sum_i X[b][k][i] * Wk[k][i][o].
+// K2 -- per-mode complex channel mix on the tensor cores:  Y[k][b][o] = sum_i X[k][b][i] * Wk[k][i][o].
 //
 // Replaces the two torch.einsum("bixy,ioxy->boxy") corner products plus the zero-filled
 // (B,32,64,33) cfloat buffer of the reference (src/models/fno/fno2d.py:54-57, 65-78).
 //
-// Weight reuse is the whole point of having this as its own phase (SURVEY.md 7 "hard parts"): the
-// 2.36 MB of spectral weights per layer are read once per *batch tile*, not once per sample.  A warp
-// owns one mode k and keeps Wk[k][:,o] for its lane's output channel o in registers (32 complex =
-// 64 regs); the 32 input-channel values of each sample are staged through shared memory and
-// broadcast.  Also used for the backward pass with the conj-transposed pack (see fno_pack.cu).
+// Modes are stored mode-major (xm[k][b][c], written that way by dft_fwd_kernel), so the 128 rows of a tile are one
+// contiguous 32 KB block; with the sample-major layout the same rows sat 73,728 B apart and both this kernel and its
+// CUDA-core predecessor were bound by that access pattern (~20 us per launch at B=256 whatever the arithmetic).
+// For one mode k the mix over a tile of 128 samples is a real GEMM on the interleaved complex64 rows exactly
+// as they sit in memory:
+//     D[128 samples][64 = (o, re|im)] = A[128][64 = (i, re|im)] * B_k^T         (tcgen05.mma kind::tf32, K = 64)
+//     B_k[(o,re)][(i,re)] = Wre,  B_k[(o,re)][(i,im)] = -Wim,  B_k[(o,im)][(i,re)] = Wim,  B_k[(o,im)][(i,im)] = Wre
+// run as 3xTF32 (hi*hi + lo*hi + hi*lo).  The B operand of every mode is prepared once per weight update
+// (pack_mix_operand_kernel: real-expanded, split into tf32 hi/lo, laid out as the K-major UMMA image) and arrives
+// with ONE 32 KB bulk copy per tile; the activations-side rows are prefetched into registers one tile ahead
+// (two 256-byte rows per warp instruction), split and stored as the A operand.  The A operand's K-direction core
+// matrix stride (LBO) is skewed by 16 B so that the 16-byte stores of lanes running along K are bank-conflict free.
+// Persistent CTA = two independent 256-thread pipelines, accumulators double-buffered in TMEM; the epilogue writes
+// 128 contiguous bytes per thread.  With the conj-transposed pack the same kernel is the adjoint mix of the
+// backward pass (Xbar[b,i,k] = sum_o G[b,o,k] conj(W[i,o,k])).
+//
+// (The CUDA-core version of this phase -- weights in registers, FFMA2 -- is in the history up to commit 73b34cc:
+// 20.7 us per launch at B=256 against the ~6 us its 40 MB of HBM traffic need.)
 #include "fno_common.cuh"
+#include "tc_common.cuh"
 
 namespace fno {
 
-constexpr int kMixWarps = 4;
-constexpr int kMixThreads = kMixWarps * 32;
-constexpr int kMixChunk = 8;        // samples staged per warp iteration
-constexpr int kMixTile = 128;       // samples per CTA (32 per warp: the 8 KB weight column load is amortised)
+constexpr int kMxThreads = 512;  // two independent 256-thread tile pipelines
+constexpr int kMxGroup = 256;
+constexpr int kMxM = 128;        // samples per tile
+constexpr int kMxK = 2 * kC;     // 64 real (i, re|im)
+constexpr int kMxN = 2 * kC;     // 64 real (o, re|im)
+constexpr uint32_t kMxLboA = (kMxM / 8) * 128 + 16;  // 2064: skewed K-direction core-matrix stride of A
+constexpr uint32_t kMxLboB = (kMxN / 8) * 128;       // 1024
+constexpr int kMxAFloats = (kMxK / 4) * kMxLboA / 4; // 8256
+constexpr int kMxBFloats = kMxN * kMxK;              // 4096 per image (hi or lo)
+constexpr int kMxOperandFloats = 2 * kMxBFloats;     // per mode: hi image then lo image (32 KB)
+constexpr int kMxReps = (kMxM * kMxK / 4) / kMxGroup;  // 8 float4 per thread per tile
 
-__global__ void __launch_bounds__(kMixThreads)
-    mode_mix_kernel(const float2* __restrict__ xm, const float2* __restrict__ wk, float2* __restrict__ ym,
-                    int batch) {
-  __shared__ __align__(16) float2 xs[kMixWarps][kMixChunk][kC];
-  const int k = blockIdx.x;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+struct MxSmem {
+  alignas(128) float a_hi[2][kMxAFloats];       // [pipeline] 2 x 33,024 B
+  alignas(128) float a_lo[2][kMxAFloats];
+  alignas(128) float b[2][kMxOperandFloats];    // [pipeline] 2 x 32 KB, bulk-copied per tile
+  alignas(8) uint64_t mma_bar[2][2];
+  alignas(8) uint64_t b_bar[2];
+  uint32_t tmem_base;
+};
 
-  // this lane's column of the 32x32 complex weight block of mode k
-  float2 w[kC];
-  const float2* wk_k = wk + static_cast<size_t>(k) * kC * kC;
-#pragma unroll
-  for (int i = 0; i < kC; ++i) w[i] = __ldg(wk_k + i * kC + lane);
-  pdl_wait();  // the weight column above is not produced by the chain; xm is
-  pdl_launch_dependents();
+// float index of A element (row m, column kk) with kk a multiple of 4
+__device__ __forceinline__ uint32_t mx_a_offset(int m, int kk) {
+  return (static_cast<uint32_t>(kk >> 2) * kMxLboA + static_cast<uint32_t>(m >> 3) * 128u + static_cast<uint32_t>(m & 7) * 16u) >> 2;
+}
 
-  const int per_warp = kMixTile / kMixWarps;
-  const int b_begin = blockIdx.y * kMixTile + warp * per_warp;
-  const int b_end = min(b_begin + per_warp, batch);
+struct MxRegs {
+  float4 v[kMxReps];  // task = rep*256 + gtid -> (row m = task >> 4, 16-byte chunk = task & 15)
+};
 
-  // software pipeline: the next chunk's rows are in flight while the current one is multiplied
-  auto load_chunk = [&](float2* st, int b0) {
+__device__ __forceinline__ void mx_prefetch(MxRegs& r, const float4* __restrict__ xm, int k, int b0, int batch, int gtid) {
 #pragma unroll
-    for (int s = 0; s < kMixChunk; ++s)
-      st[s] = (b0 + s < b_end) ? __ldg(xm + (static_cast<size_t>(b0 + s) * kModes + k) * kC + lane)
-                               : make_float2(0.f, 0.f);
-  };
-  float2 stage[kMixChunk];
-  if (b_begin < b_end) load_chunk(stage, b_begin);
-
-  for (int b0 = b_begin; b0 < b_end; b0 += kMixChunk) {
-    const int nb = min(kMixChunk, b_end - b0);
-    __syncwarp();  // previous chunk's broadcast reads are done
-#pragma unroll
-    for (int s = 0; s < kMixChunk; ++s) xs[warp][s][lane] = stage[s];
-    __syncwarp();
-    if (b0 + kMixChunk < b_end) load_chunk(stage, b0 + kMixChunk);
-
-    // acc_a += xr * (wr, wi);  acc_b += xi * (wr, wi);  y = (a.x - b.y, a.y + b.x)
-    float2 acc_a[kMixChunk], acc_b[kMixChunk];
-#pragma unroll
-    for (int s = 0; s < kMixChunk; ++s) acc_a[s] = acc_b[s] = make_float2(0.f, 0.f);
-#pragma unroll
-    for (int i = 0; i < kC; i += 2) {
-#pragma unroll
-      for (int s = 0; s < kMixChunk; ++s) {
-        const float4 v = *reinterpret_cast<const float4*>(&xs[warp][s][i]);  // broadcast: (xr0, xi0, xr1, xi1)
-        acc_a[s] = __ffma2_rn(make_float2(v.x, v.x), w[i], acc_a[s]);
-        acc_b[s] = __ffma2_rn(make_float2(v.y, v.y), w[i], acc_b[s]);
-        acc_a[s] = __ffma2_rn(make_float2(v.z, v.z), w[i + 1], acc_a[s]);
-        acc_b[s] = __ffma2_rn(make_float2(v.w, v.w), w[i + 1], acc_b[s]);
-      }
-    }
-#pragma unroll
-    for (int s = 0; s < kMixChunk; ++s)
-      if (s < nb)
-        ym[(static_cast<size_t>(b0 + s) * kModes + k) * kC + lane] =
-            make_float2(acc_a[s].x - acc_b[s].y, acc_a[s].y + acc_b[s].x);
+  for (int rep = 0; rep < kMxReps; ++rep) {
+    const int task = rep * kMxGroup + gtid;
+    const int m = task >> 4, ch = task & 15;
+    r.v[rep] = (b0 + m < batch) ? __ldg(xm + (static_cast<size_t>(k) * batch + b0 + m) * (kC / 2) + ch)
+                                : make_float4(0.f, 0.f, 0.f, 0.f);
   }
 }
 
-cudaError_t launch_mode_mix(const void* xm, const void* wk, void* ym, int batch, cudaStream_t stream) {
-  dim3 grid(kModes, (batch + kMixTile - 1) / kMixTile);
-  return launch_chained(mode_mix_kernel, grid, dim3(kMixThreads), 0, stream, static_cast<const float2*>(xm),
-                        static_cast<const float2*>(wk), static_cast<float2*>(ym), batch);
+__device__ __forceinline__ void mx_split_store(const MxRegs& r, float* a_hi, float* a_lo, int gtid) {
+#pragma unroll
+  for (int rep = 0; rep < kMxReps; ++rep) {
+    const int task = rep * kMxGroup + gtid;
+    const int m = task >> 4, ch = task & 15;
+    float4 hi, lo;
+    tc::split_tf32(r.v[rep].x, hi.x, lo.x);
+    tc::split_tf32(r.v[rep].y, hi.y, lo.y);
+    tc::split_tf32(r.v[rep].z, hi.z, lo.z);
+    tc::split_tf32(r.v[rep].w, hi.w, lo.w);
+    const uint32_t off = mx_a_offset(m, 4 * ch);
+    *reinterpret_cast<float4*>(a_hi + off) = hi;
+    *reinterpret_cast<float4*>(a_lo + off) = lo;
+  }
 }
+
+template <int GRP>
+__device__ __forceinline__ void mx_group_barrier() {
+  asm volatile("bar.sync %0, %1;" ::"n"(GRP + 1), "n"(kMxGroup) : "memory");
+}
+
+template <int GRP>
+__device__ __forceinline__ void mx_pipeline(MxSmem& sm, const float4* __restrict__ xm, const float* __restrict__ wop,
+                                            float4* __restrict__ ym, int batch, int n_btiles, int n_tiles) {
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int gtid = tid & (kMxGroup - 1), gwarp = tc::warp_index_uniform() & 7;
+  const uint32_t tmem_base = sm.tmem_base + GRP * (2 * kMxN);
+  constexpr uint32_t idesc = tc::make_idesc_tf32(kMxM, kMxN);
+
+  const int first = blockIdx.x, stride = gridDim.x;
+  const int n_cta = (first < n_tiles) ? (n_tiles - first + stride - 1) / stride : 0;
+  const int n_mine = (n_cta + 1 - GRP) / 2;
+  auto tile_of = [&](int it) { return first + (2 * it + GRP) * stride; };  // tile = k * n_btiles + sample tile
+
+  // epilogue of local tile `it`: warps w and w+4 share TMEM lane quadrant w & 3 (rows 32(w&3)..+31 of the tile) and
+  // take the 32-float column halves; a thread writes 128 contiguous bytes of its sample's output row
+  auto epilogue = [&](int it) {
+    const int buf = it & 1;
+    mbar_wait(&sm.mma_bar[GRP][buf], (it >> 1) & 1);
+    tc::fence_after_thread_sync();
+    const int quad = gwarp & 3, half = gwarp >> 2;
+    const int tile = tile_of(it);
+    const int k = tile / n_btiles, b = (tile % n_btiles) * kMxM + quad * 32 + lane;
+    float v[32];
+    tc::tmem_ld32(tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + buf * kMxN + half * 32, v);
+    tc::fence_before_thread_sync();
+    if (b < batch) {
+      float4* dst = ym + (static_cast<size_t>(k) * batch + b) * (kC / 2) + half * 8;
+#pragma unroll
+      for (int c = 0; c < 8; ++c) dst[c] = make_float4(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
+    }
+  };
+
+  // Two tiles of activations are in flight in registers (at B = 256 a pipeline owns only ~2 tiles, so every
+  // load of the kernel is issued up front and the DRAM latency is paid once, not once per tile).
+  MxRegs ring[2];
+  auto prefetch_tile = [&](MxRegs& r, int it) {
+    if (it < n_mine) {
+      const int t = tile_of(it);
+      mx_prefetch(r, xm, t / n_btiles, (t % n_btiles) * kMxM, batch, gtid);
+    }
+  };
+  prefetch_tile(ring[0], 0);
+  prefetch_tile(ring[1], 1);
+
+  auto body = [&](int it, MxRegs& regs) {
+    const int buf = it & 1;
+    const int tile = tile_of(it);
+    // the single-buffered operands were last read by the MMAs of tile it-1: wait for them (normally long done)
+    if (it >= 1) mbar_wait(&sm.mma_bar[GRP][(it - 1) & 1], ((it - 1) >> 1) & 1);
+    if (it >= 1 && gwarp == 0 && tc::elect_one()) {  // this tile's B operand: one bulk copy (tile 0: kernel prologue)
+      constexpr uint32_t kBytes = kMxOperandFloats * sizeof(float);
+      mbar_expect_tx(&sm.b_bar[GRP], kBytes);
+      bulk_g2s(sm.b[GRP], wop + static_cast<size_t>(tile / n_btiles) * kMxOperandFloats, kBytes, &sm.b_bar[GRP]);
+    }
+    mx_split_store(regs, sm.a_hi[GRP], sm.a_lo[GRP], gtid);
+    tc::fence_proxy_async_smem();
+    tc::fence_before_thread_sync();
+    mx_group_barrier<GRP>();
+    tc::fence_after_thread_sync();
+    // refill this register set AFTER the fence: the membar inside fence.proxy.async would otherwise wait for the loads
+    prefetch_tile(regs, it + 2);
+    if (gwarp == 0) {
+      if (tc::elect_one()) {
+        mbar_wait(&sm.b_bar[GRP], it & 1);
+        const uint32_t d_tmem = tmem_base + buf * kMxN;
+        const uint32_t a_s[3] = {tc::smem_addr(sm.a_hi[GRP]), tc::smem_addr(sm.a_lo[GRP]), tc::smem_addr(sm.a_hi[GRP])};
+        const uint32_t b_hi = tc::smem_addr(sm.b[GRP]), b_lo = b_hi + kMxBFloats * sizeof(float);
+        const uint32_t b_s[3] = {b_hi, b_hi, b_lo};
+#pragma unroll
+        for (int pass = 0; pass < 3; ++pass) {
+          const uint64_t da0 = tc::make_smem_desc(a_s[pass], kMxLboA, 128);
+          const uint64_t db0 = tc::make_smem_desc(b_s[pass], kMxLboB, 128);
+#pragma unroll
+          for (int ks = 0; ks < kMxK / 8; ++ks) {
+            const uint64_t da = da0 + ((ks * 2 * kMxLboA) >> 4), db = db0 + ((ks * 2 * kMxLboB) >> 4);
+            if (pass == 0 && ks == 0) tc::mma_tf32_imm<false>(d_tmem, da, db, idesc);
+            else tc::mma_tf32_imm<true>(d_tmem, da, db, idesc);
+          }
+        }
+        tc::mma_commit(&sm.mma_bar[GRP][buf]);
+      }
+      __syncwarp();
+    }
+    if (it >= 1) epilogue(it - 1);
+  };
+  for (int it = 0; it < n_mine; it += 2) {
+    body(it, ring[0]);
+    if (it + 1 < n_mine) body(it + 1, ring[1]);
+  }
+  if (n_mine >= 1) epilogue(n_mine - 1);
+}
+
+__global__ void __launch_bounds__(kMxThreads, 1)
+    mode_mix_tc_kernel(const float4* __restrict__ xm, const float* __restrict__ wop, float4* __restrict__ ym, int batch,
+                       int n_btiles, int n_tiles) {
+  extern __shared__ __align__(1024) unsigned char smem_raw[];  // no pointer arithmetic: keeps LDS/STS addressing
+  MxSmem& sm = *reinterpret_cast<MxSmem*>(smem_raw);
+  if ((smem_u32(smem_raw) & 127u) != 0) __trap();
+  const int tid = threadIdx.x, warp = tc::warp_index_uniform();
+  const int grp = warp >> 3;
+  if (tid == 0) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) mbar_init(&sm.mma_bar[i >> 1][i & 1], 1);
+    mbar_init(&sm.b_bar[0], 1);
+    mbar_init(&sm.b_bar[1], 1);
+    fence_mbar_init();
+  }
+  if (warp == 0) tc::tmem_alloc<4 * kMxN>(&sm.tmem_base);
+  tc::fence_before_thread_sync();
+  __syncthreads();
+  tc::fence_after_thread_sync();
+  if (tid == 0) {  // the first tile's weights of both pipelines do not depend on the previous kernel: fetch them now
+    constexpr uint32_t kBytes = kMxOperandFloats * sizeof(float);
+#pragma unroll
+    for (int g = 0; g < 2; ++g) {
+      const int t = blockIdx.x + g * gridDim.x;
+      if (t < n_tiles) {
+        mbar_expect_tx(&sm.b_bar[g], kBytes);
+        bulk_g2s(sm.b[g], wop + static_cast<size_t>(t / n_btiles) * kMxOperandFloats, kBytes, &sm.b_bar[g]);
+      }
+    }
+  }
+  pdl_wait();  // xm comes from the previous kernel of the chain
+  pdl_launch_dependents();
+  if (grp == 0) mx_pipeline<0>(sm, xm, wop, ym, batch, n_btiles, n_tiles);
+  else mx_pipeline<1>(sm, xm, wop, ym, batch, n_btiles, n_tiles);
+  tc::fence_before_thread_sync();
+  __syncthreads();
+  if (warp == 0) tc::tmem_dealloc<4 * kMxN>(sm.tmem_base);
+}
+
+cudaError_t launch_mode_mix(const void* xm, const void* wop, void* ym, int batch, cudaStream_t stream) {
+  auto kern = mode_mix_tc_kernel;
+  constexpr size_t smem = sizeof(MxSmem);
+  static bool configured = false;
+  static int n_sm = 0;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    e = cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
+    if (e != cudaSuccess) return e;
+    configured = true;
+  }
+  const int n_btiles = (batch + kMxM - 1) / kMxM;
+  const int n_tiles = kModes * n_btiles;
+  const int grid = n_tiles < 2 * n_sm ? (n_tiles + 1) / 2 : n_sm;
+  return launch_chained(kern, dim3(grid), dim3(kMxThreads), smem, stream, static_cast<const float4*>(xm),
+                        static_cast<const float*>(wop), static_cast<float4*>(ym), batch, n_btiles, n_tiles);
+}
+
+// ------------------------------------------------------------------------------------------------
+// B operand image of the mix, built from the packed weights Wk[k][i][o] (pack_spectral_kernel below):
+// per mode 2 x 4096 floats (tf32 hi image, then lo image), element (n = 2o + part, kk = 2i + ri) at
+// tc::kmajor_offset(n, kk, 64).
+// ------------------------------------------------------------------------------------------------
+__global__ void pack_mix_operand_kernel(const float2* __restrict__ wk, float* __restrict__ wop) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;  // over k*1024 + i*32 + o
+  if (idx >= kModes * kC * kC) return;
+  const int k = idx / (kC * kC), i = (idx / kC) % kC, o = idx % kC;
+  const float2 w = wk[idx];
+  float* img = wop + static_cast<size_t>(k) * kMxOperandFloats;
+  const float val[2][2] = {{w.x, -w.y}, {w.y, w.x}};  // [part of the output][re|im of the input]
+#pragma unroll
+  for (int part = 0; part < 2; ++part)
+#pragma unroll
+    for (int ri = 0; ri < 2; ++ri) {
+      float hi, lo;
+      tc::split_tf32(val[part][ri], hi, lo);
+      const uint32_t off = tc::kmajor_offset(2 * o + part, 2 * i + ri, kMxN) / 4;
+      img[off] = hi;
+      img[kMxBFloats + off] = lo;
+    }
+}
+
+cudaError_t launch_pack_mix_operand(const void* wk, void* wop, cudaStream_t stream) {
+  const int n = kModes * kC * kC;
+  pack_mix_operand_kernel<<<(n + 255) / 256, 256, 0, stream>>>(static_cast<const float2*>(wk), static_cast<float*>(wop));
+  return cudaGetLastError();
+}
+
+size_t mix_operand_bytes() { return static_cast<size_t>(kModes) * kMxOperandFloats * sizeof(float); }
 
 // ------------------------------------------------------------------------------------------------
 // Weight packing: reference parameter layout (Cin, Cout, 12, 12) complex64 x2 (weights1, weights2;

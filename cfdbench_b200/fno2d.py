@@ -186,10 +186,7 @@ class Fno2d(AutoCfdModel):
             pk = {"wk": [], "w0t": [], "wkT": None}
             st = self._stream()
             for blk in self.blocks:
-                wk = torch.empty(NMODES, HIDDEN, HIDDEN, dtype=torch.complex64, device=dev)
-                _lib.check(lib.fno_pack_spectral_weights(blk.conv0.weights1.data_ptr(), blk.conv0.weights2.data_ptr(),
-                                                         wk.data_ptr(), 0, st), "fno_pack_spectral_weights")
-                pk["wk"].append(wk)
+                pk["wk"].append(self._mix_operand(blk, 0))
                 pk["w0t"].append(blk.w0.weight.detach().view(HIDDEN, HIDDEN).t().contiguous())
             if "gx" not in self._packed:
                 lin = torch.tensor(np.linspace(0, 1, H), dtype=torch.float)  # as reference fno2d.py:250-252
@@ -216,14 +213,23 @@ class Fno2d(AutoCfdModel):
             pk["wkT"] = []
             wb = _lib.FnoWeightsBwd()
             for l, blk in enumerate(self.blocks):
-                wkT = torch.empty(NMODES, HIDDEN, HIDDEN, dtype=torch.complex64, device=self.device)
-                _lib.check(lib.fno_pack_spectral_weights(blk.conv0.weights1.data_ptr(), blk.conv0.weights2.data_ptr(),
-                                                         wkT.data_ptr(), 1, st), "fno_pack_spectral_weights(T)")
+                wkT = self._mix_operand(blk, 1)
                 pk["wkT"].append(wkT)
                 wb.spec_wkT[l] = wkT.data_ptr()
                 wb.w0[l] = blk.w0.weight.data_ptr()
             pk["struct_bwd"] = wb
         return pk
+
+    def _mix_operand(self, blk: "FnoBlock", conj_transpose: int) -> Tensor:
+        """weights1/2 -> packed [288][32][32] complex -> the tensor-core operand image fno_mode_mix consumes."""
+        lib = _lib.load()
+        st = self._stream()
+        wk = torch.empty(NMODES, HIDDEN, HIDDEN, dtype=torch.complex64, device=self.device)
+        _lib.check(lib.fno_pack_spectral_weights(blk.conv0.weights1.data_ptr(), blk.conv0.weights2.data_ptr(),
+                                                 wk.data_ptr(), conj_transpose, st), "fno_pack_spectral_weights")
+        wop = torch.empty(lib.fno_mix_operand_bytes(), dtype=torch.uint8, device=self.device)
+        _lib.check(lib.fno_pack_mix_operand(wk.data_ptr(), wop.data_ptr(), st), "fno_pack_mix_operand")
+        return wop
 
     def _workspace(self, batch: int, slot: int = 0):
         key = (batch, self.act_dtype, self.device, slot)
@@ -234,8 +240,8 @@ class Fno2d(AutoCfdModel):
             bufs = dict(
                 act0=torch.empty(batch, HIDDEN, H, W, dtype=adt, device=dev),
                 act1=torch.empty(batch, HIDDEN, H, W, dtype=adt, device=dev),
-                xm=torch.empty(batch, NMODES, HIDDEN, dtype=torch.complex64, device=dev),
-                ym=torch.empty(batch, NMODES, HIDDEN, dtype=torch.complex64, device=dev),
+                xm=torch.empty(NMODES, batch, HIDDEN, dtype=torch.complex64, device=dev),
+                ym=torch.empty(NMODES, batch, HIDDEN, dtype=torch.complex64, device=dev),
                 z=torch.empty(batch, H, 2 * MODES, HIDDEN, dtype=torch.float32, device=dev),
             )
             st = _lib.FnoWorkspace()
@@ -284,7 +290,7 @@ class Fno2d(AutoCfdModel):
         adt = self._act_torch_dtype()
         acts = [torch.empty(b, HIDDEN, H, W, dtype=adt, device=dev) for _ in range(L + 1)]
         pres = [torch.empty(b, HIDDEN, H, W, dtype=torch.float32, device=dev) for _ in range(L)]
-        xms = [torch.empty(b, NMODES, HIDDEN, dtype=torch.complex64, device=dev) for _ in range(L)]
+        xms = [torch.empty(NMODES, b, HIDDEN, dtype=torch.complex64, device=dev) for _ in range(L)]
         sv = _lib.FnoTrainSaved()
         for l in range(L + 1):
             sv.act[l] = acts[l].data_ptr()
@@ -329,7 +335,7 @@ class Fno2d(AutoCfdModel):
         d0 = torch.empty(b, HIDDEN, H, W, dtype=torch.float32, device=dev)
         d1 = torch.empty(b, HIDDEN, H, W, dtype=torch.float32, device=dev)
         dz1 = torch.empty(min(b, _lib.BWD_CHUNK), PROJ, H, W, dtype=torch.float32, device=dev)
-        gm = torch.empty(b, NMODES, HIDDEN, dtype=torch.complex64, device=dev)
+        gm = torch.empty(NMODES, b, HIDDEN, dtype=torch.complex64, device=dev)
         gwk = torch.empty(NMODES, HIDDEN, HIDDEN, dtype=torch.complex64, device=dev)
         sc = _lib.FnoBwdScratch()
         sc.d[0], sc.d[1] = d0.data_ptr(), d1.data_ptr()

@@ -17,9 +17,11 @@
  *   frames / preds   [B][2][64][64]    float32
  *   mask             [B][64][64]       float32  (a (B,1,64,64) tensor has the same layout)
  *   case_params      [B][p]            float32
- *   modes (xm, ym)   [B][288][32]      complex64 (interleaved re,im); mode k = kxi*12 + ky,
+ *   modes (xm, ym)   [288][B][32]      complex64 (interleaved re,im), MODE-major; mode k = kxi*12 + ky,
  *                                      kxi 0..11 <-> kx 0..11 (weights1), kxi 12..23 <-> kx 52..63 (weights2)
  *   packed spectral  [288][32 in][32 out] complex64 (fno_pack_spectral_weights)
+ *   mix operand      per mode 2 x [64 = (out, re|im)][64 = (in, re|im)] float32: the real-expanded block as tf32
+ *                    hi / lo images in the tensor core's K-major operand layout (fno_pack_mix_operand)
  *   w0t              [32 in][32 out]   float32  (transpose of the Conv2d weight (out,in,1,1))
  */
 #ifndef CFDBENCH_B200_H_
@@ -45,7 +47,7 @@ typedef struct fno_weights {
   int32_t n_case_params; /* p: 5 cavity, 8 cylinder (reference src/utils/autoregressive.py:31-37) */
   const float* fc0_w;    /* [32][5+p]  fc0.weight  (reference fno2d.py:150-156) */
   const float* fc0_b;    /* [32] */
-  const void* spec_wk[FNO_MAX_LAYERS]; /* packed blocks.{l}.conv0.weights1/2 */
+  const void* spec_wk[FNO_MAX_LAYERS]; /* mix operand of blocks.{l}.conv0.weights1/2 (fno_pack_mix_operand) */
   const float* w0t[FNO_MAX_LAYERS];    /* blocks.{l}.w0.weight transposed */
   const float* w0_b[FNO_MAX_LAYERS];   /* blocks.{l}.w0.bias */
   const float* fc1_w;    /* [128][32] fc1.weight */
@@ -74,6 +76,10 @@ size_t fno_z_bytes(int batch);
 /* weights1, weights2: (32,32,12,12) complex64 as stored by the reference (fno2d.py:31-51).
  * conj_transpose=0 -> wk[k][i][o] = W[i][o][k] (forward); 1 -> wk[k][o][i] = conj(W[i][o][k]) (adjoint). */
 int fno_pack_spectral_weights(const void* weights1, const void* weights2, void* wk, int conj_transpose, void* stream);
+/* packed weights wk[288][32][32] -> the operand image fno_mode_mix consumes (fno_mix_operand_bytes() bytes).
+ * Run once per weight update; for the adjoint mix feed it the conj_transpose=1 pack. */
+size_t fno_mix_operand_bytes(void);
+int fno_pack_mix_operand(const void* wk, void* wop, void* stream);
 /* gradient wrt packed forward weights [288][32][32] -> gradients of weights1 / weights2 */
 int fno_unpack_spectral_grads(const void* gwk, void* gw1, void* gw2, void* stream);
 
@@ -84,8 +90,8 @@ int fno_lift_fwd(const float* inputs, const float* mask, const float* case_param
 /* The four phases of SpectralConv2d_fast + FnoBlock (reference fno2d.py:59-82, 106-112):            */
 /* (1) torch.fft.rfft2 restricted to the kept modes (fno2d.py:62,73-78); outputs scaled by s0 (ky=0), s1 (ky>0) */
 int fno_spectral_dft_fwd(const void* act_in, void* xm, int batch, int act_dtype, float s0, float s1, void* stream);
-/* (2) einsum("bixy,ioxy->boxy") on both corners (fno2d.py:54-57,73-78) */
-int fno_mode_mix(const void* xm, const void* wk, void* ym, int batch, void* stream);
+/* (2) einsum("bixy,ioxy->boxy") on both corners (fno2d.py:54-57,73-78); wop = fno_pack_mix_operand image */
+int fno_mode_mix(const void* xm, const void* wop, void* ym, int batch, void* stream);
 /* (3) first half of irfft2 on the zero-padded spectrum (fno2d.py:65-72,81): inverse C2C along kx of the 24 kept
  *     rows, scaled by s0 (ky=0) / s1 (ky>0) (forward: 1/4096, 2/4096): z[b][h][2 ky + (re|im)][o], fno_z_bytes(B). */
 int fno_spectral_inv_kx(const void* ym, void* z, int batch, float s0, float s1, void* stream);
@@ -130,7 +136,7 @@ typedef struct fno_train_saved {
 
 /* Extra weight views the backward pass needs. */
 typedef struct fno_weights_bwd {
-  const void* spec_wkT[FNO_MAX_LAYERS]; /* fno_pack_spectral_weights(..., conj_transpose=1) */
+  const void* spec_wkT[FNO_MAX_LAYERS]; /* mix operand of fno_pack_spectral_weights(..., conj_transpose=1) */
   const float* w0[FNO_MAX_LAYERS];      /* blocks.{l}.w0.weight in its natural [out][in] layout */
 } fno_weights_bwd;
 

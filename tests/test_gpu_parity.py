@@ -71,9 +71,9 @@ def test_dft_fwd_kernel(lib, batch):
     rng = np.random.default_rng(0)
     x = rng.standard_normal((batch, 32, 64, 64)).astype(np.float32)
     xd = dev(x)
-    xm = torch.zeros(batch, 288, 32, dtype=torch.complex64, device="cuda")
+    xm = torch.zeros(288, batch, 32, dtype=torch.complex64, device="cuda")  # mode-major: [k][b][c]
     _lib.check(lib.fno_spectral_dft_fwd(xd.data_ptr(), xm.data_ptr(), batch, _lib.ACT_F32, 1.0, 1.0, stream()), "dft")
-    ref = onp.spectral_modes(x, 12, 12).reshape(batch, 32, 288).transpose(0, 2, 1)  # [b][k][c]
+    ref = onp.spectral_modes(x, 12, 12).reshape(batch, 32, 288).transpose(2, 0, 1)  # [k][b][c]
     got = xm.cpu().numpy()
     err = np.linalg.norm(got - ref) / np.linalg.norm(ref)
     assert err < 2e-6, err
@@ -81,7 +81,7 @@ def test_dft_fwd_kernel(lib, batch):
     _lib.check(lib.fno_spectral_dft_fwd(xd.data_ptr(), xm.data_ptr(), batch, _lib.ACT_F32, 0.25, 0.5, stream()), "dft")
     c = np.full(12, 0.5)
     c[0] = 0.25
-    ref2 = (onp.spectral_modes(x, 12, 12) * c).reshape(batch, 32, 288).transpose(0, 2, 1)
+    ref2 = (onp.spectral_modes(x, 12, 12) * c).reshape(batch, 32, 288).transpose(2, 0, 1)
     err = np.linalg.norm(xm.cpu().numpy() - ref2) / np.linalg.norm(ref2)
     assert err < 2e-6, err
 
@@ -89,20 +89,40 @@ def test_dft_fwd_kernel(lib, batch):
 def test_mode_mix_and_pack_kernels(lib):
     from cfdbench_b200 import _lib
     rng = np.random.default_rng(1)
-    batch = 70  # crosses the 64-sample CTA tile and leaves a ragged tail
+    batch = 200  # crosses the 128-sample tile and leaves a ragged tail
     sd = synth.make_state_dict(3, spectral_gain=100.0)
     w1, w2 = sd["blocks.0.conv0.weights1"], sd["blocks.0.conv0.weights2"]
-    xm = (rng.standard_normal((batch, 288, 32)) + 1j * rng.standard_normal((batch, 288, 32))).astype(np.complex64)
+    xm = (rng.standard_normal((288, batch, 32)) + 1j * rng.standard_normal((288, batch, 32))).astype(np.complex64)
     wk = torch.empty(288, 32, 32, dtype=torch.complex64, device="cuda")
     w1d, w2d, xmd = dev(w1), dev(w2), dev(xm)  # keep alive: the calls are asynchronous
     _lib.check(lib.fno_pack_spectral_weights(w1d.data_ptr(), w2d.data_ptr(), wk.data_ptr(), 0, stream()), "pack")
     wt = onp.stack_weights(w1, w2).reshape(32, 32, 288)  # [i][o][k]
     np.testing.assert_array_equal(wk.cpu().numpy(), wt.transpose(2, 0, 1).astype(np.complex64))
-    ym = torch.zeros(batch, 288, 32, dtype=torch.complex64, device="cuda")
-    _lib.check(lib.fno_mode_mix(xmd.data_ptr(), wk.data_ptr(), ym.data_ptr(), batch, stream()), "mix")
-    ref = np.einsum("bki,iok->bko", xm.astype(np.complex128), wt)
+    # tensor-core operand image: per mode [hi | lo] x [n = (o, part)][kk = (i, re|im)] in K-major core matrices
+    wop = torch.empty(lib.fno_mix_operand_bytes(), dtype=torch.uint8, device="cuda")
+    assert wop.numel() == 288 * 2 * 64 * 64 * 4
+    _lib.check(lib.fno_pack_mix_operand(wk.data_ptr(), wop.data_ptr(), stream()), "pack operand")
+    img = wop.cpu().numpy().view(np.float32).reshape(288, 2, 16, 8, 8, 4)  # [k][hi|lo][kk/4][n/8][n%8][kk%4]
+    full = img.transpose(0, 1, 3, 4, 2, 5).reshape(288, 2, 64, 64).astype(np.float64)  # [k][hi|lo][n][kk]
+    expand = np.empty((288, 64, 64))
+    wkn = wt.transpose(2, 0, 1)  # [k][i][o]
+    expand[:, 0::2, 0::2] = wkn.real.transpose(0, 2, 1)
+    expand[:, 0::2, 1::2] = -wkn.imag.transpose(0, 2, 1)
+    expand[:, 1::2, 0::2] = wkn.imag.transpose(0, 2, 1)
+    expand[:, 1::2, 1::2] = wkn.real.transpose(0, 2, 1)
+    assert np.abs(full.sum(1) - expand).max() <= 2.0 ** -21 * np.abs(expand).max()
+    assert np.all((img.view(np.uint32) & 0x1FFF) == 0)  # both images are exact tf32 values
+    ym = torch.zeros(288, batch, 32, dtype=torch.complex64, device="cuda")
+    _lib.check(lib.fno_mode_mix(xmd.data_ptr(), wop.data_ptr(), ym.data_ptr(), batch, stream()), "mix")
+    ref = np.einsum("kbi,iok->kbo", xm.astype(np.complex128), wt)
     err = np.linalg.norm(ym.cpu().numpy() - ref) / np.linalg.norm(ref)
     assert err < 2e-6, err
+    # small batch: one partially filled tile
+    xm3 = dev(np.ascontiguousarray(xm[:, :3]))
+    ym1 = torch.zeros(288, 3, 32, dtype=torch.complex64, device="cuda")
+    _lib.check(lib.fno_mode_mix(xm3.data_ptr(), wop.data_ptr(), ym1.data_ptr(), 3, stream()), "mix")
+    torch.cuda.synchronize()
+    assert torch.equal(ym1, ym[:, :3])
     # adjoint pack + unpack
     wkT = torch.empty(288, 32, 32, dtype=torch.complex64, device="cuda")
     _lib.check(lib.fno_pack_spectral_weights(w1d.data_ptr(), w2d.data_ptr(), wkT.data_ptr(), 1, stream()), "packT")
@@ -124,7 +144,7 @@ def test_block_out_kernel(lib, epi):
     w0 = (rng.standard_normal((32, 32)) / 6).astype(np.float32)
     bias = rng.standard_normal(32).astype(np.float32)
     pre_in = rng.standard_normal((batch, 32, 64, 64)).astype(np.float32)
-    ymd = dev(ym.reshape(batch, 32, 288).transpose(0, 2, 1).astype(np.complex64))  # [b][k][o]
+    ymd = dev(np.ascontiguousarray(ym.reshape(batch, 32, 288).transpose(2, 0, 1)).astype(np.complex64))  # [k][b][o]
     out = torch.zeros(batch, 32, 64, 64, device="cuda")
     pre_out = torch.zeros(batch, 32, 64, 64, device="cuda")
     code = {"gelu": _lib.EPI_GELU, "save_pre": _lib.EPI_GELU_SAVE_PRE, "mul_dgelu": _lib.EPI_MUL_DGELU,
