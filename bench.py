@@ -38,9 +38,10 @@ sys.path.insert(0, ROOT)
 from cfdbench_b200 import dp, synth  # noqa: E402
 
 # dram__bytes_read.sum + dram__bytes_write.sum of one block_tc_kernel launch at B=256 from the `ncu --set full`
-# capture summarised in profiles/ncu_r01_final.md (bf16 storage: 117.6 MB read + 36.7 MB written; the read side
-# includes the fp32 Z rows produced by inv_kx_kernel that are not part of the algorithmic byte count).
-NCU_TRAFFIC_BYTES = {("bf16", 256): 154292224}
+# capture summarised in profiles/ncu_r01h.md (bf16 storage: 117.6 MB read + 35.8 MB written; the read side
+# includes the fp32 Z rows produced by inv_kx_kernel that are not part of the algorithmic byte count, and part of
+# the output is still in L2 when the kernel ends).
+NCU_TRAFFIC_BYTES = {("bf16", 256): 153320960}
 
 METRIC = "fno_rollout_steps_per_sec"
 UNIT = "steps/s"
@@ -225,15 +226,17 @@ def rel_l2_vs_oracle(model, sd, batch, steps: int = 4, nsamp: int = 2):
     return out
 
 
-def timed_train_step(p: int, batch_size: int, steps: int = 5, warmup: int = 3):
+def timed_train_step(p: int, batch_size: int, steps: int = 5, warmup: int = 3, fused_adam: bool = True):
     """fwd -> loss["nmse"].backward() -> Adam.step -> zero_grad (reference src/train_auto.py:233-260) on this GPU,
-    fp32 storage, data parallel gradient all-reduce when launched under torchrun.  Secondary number, not the metric."""
+    fp32 storage, data parallel gradient all-reduce when launched under torchrun.  Secondary number, not the metric.
+    fused_adam=False uses the optimizer the reference script builds itself (torch.optim.Adam)."""
+    from cfdbench_b200 import FusedAdam
     model, _ = build_model("f32", p)
     if torch.distributed.is_initialized():
         model.enable_data_parallel()
     batch = synth.make_batch(7, batch_size, "cavity")
     tb = {k: torch.from_numpy(v).to(model.device) for k, v in batch.items()}
-    opt = torch.optim.Adam(model.parameters(), lr=1e-4)
+    opt = (FusedAdam if fused_adam else torch.optim.Adam)(model.parameters(), lr=1e-4)
     ev = []
     for i in range(warmup + steps):
         a, z = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -250,7 +253,8 @@ def timed_train_step(p: int, batch_size: int, steps: int = 5, warmup: int = 3):
     del model
     torch.cuda.empty_cache()
     return {"value": 1e3 / ms, "unit": "train steps/s per GPU", "ms_per_step": ms, "batch_per_gpu": batch_size,
-            "what": "fwd + nmse.backward + torch.optim.Adam.step, fp32 storage"}
+            "what": "fwd + native MseLoss + nmse.backward + " + ("FusedAdam (fno_adam_step)" if fused_adam else
+                                                                   "torch.optim.Adam") + ".step, fp32 storage"}
 
 
 def cpu_baseline(sd, batch, budget_s: float = 20.0, max_steps: int = 8):
@@ -360,6 +364,7 @@ def main():
         torch.cuda.empty_cache()
 
     train = timed_train_step(p, min(args.batch, 64))  # all ranks take part (gradient all-reduce under torchrun)
+    train["torch_adam_ms_per_step"] = timed_train_step(p, min(args.batch, 64), fused_adam=False)["ms_per_step"]
     if rank != 0:
         if torch.distributed.is_initialized():
             torch.distributed.destroy_process_group()

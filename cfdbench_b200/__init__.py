@@ -8,11 +8,14 @@ Public surface mirrors the reference's for this path:
 from .base_model import AutoCfdModel
 from .loss import MseLoss, loss_name_to_fn
 
-__all__ = ["AutoCfdModel", "MseLoss", "loss_name_to_fn", "Fno2d", "FnoBlock", "SpectralConv2d_fast"]
+__all__ = ["AutoCfdModel", "MseLoss", "loss_name_to_fn", "Fno2d", "FnoBlock", "SpectralConv2d_fast", "FusedAdam"]
 
 
 def __getattr__(name):  # lazy: importing the package must not require the native library
     if name in ("Fno2d", "FnoBlock", "SpectralConv2d_fast"):
         from . import fno2d
         return getattr(fno2d, name)
+    if name == "FusedAdam":
+        from .optim import FusedAdam
+        return FusedAdam
     raise AttributeError(name)

@@ -67,6 +67,15 @@ class FnoBwdScratch(C.Structure):
 
 
 BWD_CHUNK = 32
+ADAM_MAX_TENSORS = 32
+
+
+class FnoAdamTensors(C.Structure):
+    _fields_ = [("count", C.c_int32),
+                ("param", C.c_void_p * ADAM_MAX_TENSORS), ("grad", C.c_void_p * ADAM_MAX_TENSORS),
+                ("exp_avg", C.c_void_p * ADAM_MAX_TENSORS), ("exp_avg_sq", C.c_void_p * ADAM_MAX_TENSORS),
+                ("n", C.c_int64 * ADAM_MAX_TENSORS)]
+
 
 _P = C.c_void_p
 _I = C.c_int
@@ -95,6 +104,11 @@ SIGNATURES = {
     "fno_rollout_host": (C.c_int, [C.POINTER(FnoWeights), _P, _P, _P, _P, _I, C.POINTER(FnoWorkspace), _P, _I, _I, _P]),
     "fno_rollout_host_scratch_bytes": (C.c_size_t, [_I, _I, _I]),
     "fno_multistep_metrics": (C.c_int, [_P, _P, _P, _P, _I, _I, _P]),
+    "fno_loss_scratch_bytes": (C.c_size_t, []),
+    "fno_loss_fwd": (C.c_int, [_P, _P, C.c_size_t, _P, _P, _P]),
+    "fno_loss_bwd": (C.c_int, [_P, _P, _P, _P, _P, C.c_size_t, _P]),
+    "fno_adam_step": (C.c_int, [C.POINTER(FnoAdamTensors), C.c_float, C.c_float, C.c_float, C.c_float, C.c_float,
+                                C.c_int64, _P]),
     "fno_forward_train": (C.c_int, [C.POINTER(FnoWeights), _P, _P, _P, _P, C.POINTER(FnoTrainSaved),
                                     C.POINTER(FnoWorkspace), _I, _I, _P]),
     "fno_backward": (C.c_int, [C.POINTER(FnoWeights), C.POINTER(FnoWeightsBwd), _P, _P, _P, _P,

@@ -13,6 +13,10 @@ cudaError_t launch_pack_spectral(const void*, const void*, void*, int, cudaStrea
 cudaError_t launch_unpack_spectral(const void*, void*, void*, cudaStream_t);
 cudaError_t launch_pack_mix_operand(const void*, void*, cudaStream_t);
 size_t mix_operand_bytes();
+cudaError_t launch_loss_fwd(const float*, const float*, size_t, float*, float*, cudaStream_t);
+cudaError_t launch_loss_bwd(const float*, const float*, const float*, const float*, float*, size_t, cudaStream_t);
+size_t loss_scratch_bytes();
+cudaError_t launch_adam_step(const fno_adam_tensors*, float, float, float, float, float, long long, cudaStream_t);
 cudaError_t launch_inv_kx(const void*, void*, int, float, float, cudaStream_t);
 template <typename TAct>
 cudaError_t launch_block_tc(int, const void*, const void*, const float*, const float*, void*, float*, const float*, int,
@@ -303,6 +307,34 @@ int fno_multistep_metrics(const float* preds_seq, const float* label_u, const fl
   if (!preds_seq || !label_u || !mask || !sums || steps <= 0 || batch <= 0)
     return fail(kErrArg, "fno_multistep_metrics: bad argument");
   FNO_CUDA(launch_multistep_metrics(preds_seq, label_u, mask, sums, steps, batch, S(stream)), "multistep_metrics_kernel");
+  return kOk;
+}
+
+size_t fno_loss_scratch_bytes(void) { return loss_scratch_bytes(); }
+
+int fno_loss_fwd(const float* preds, const float* labels, size_t n, void* scratch, float* out, void* stream) {
+  if (!preds || !labels || !scratch || !out || n == 0) return fail(kErrArg, "fno_loss_fwd: bad argument");
+  if ((reinterpret_cast<uintptr_t>(preds) | reinterpret_cast<uintptr_t>(labels)) & 15)
+    return fail(kErrArg, "fno_loss_fwd: preds / labels must be 16-byte aligned");
+  FNO_CUDA(launch_loss_fwd(preds, labels, n, static_cast<float*>(scratch), out, S(stream)), "loss_fwd_kernel");
+  return kOk;
+}
+
+int fno_loss_bwd(const float* preds, const float* labels, const float* fwd, const float* gout, float* dpreds, size_t n,
+                 void* stream) {
+  if (!preds || !labels || !fwd || !gout || !dpreds || n == 0) return fail(kErrArg, "fno_loss_bwd: bad argument");
+  FNO_CUDA(launch_loss_bwd(preds, labels, fwd, gout, dpreds, n, S(stream)), "loss_bwd_kernel");
+  return kOk;
+}
+
+int fno_adam_step(const fno_adam_tensors* t, float lr, float beta1, float beta2, float eps, float weight_decay,
+                  int64_t step, void* stream) {
+  if (!t || t->count < 0 || t->count > FNO_ADAM_MAX_TENSORS || step < 1)
+    return fail(kErrArg, "fno_adam_step: bad argument");
+  for (int i = 0; i < t->count; ++i)
+    if (!t->param[i] || !t->grad[i] || !t->exp_avg[i] || !t->exp_avg_sq[i] || t->n[i] <= 0)
+      return fail(kErrArg, "fno_adam_step: null tensor or empty size");
+  FNO_CUDA(launch_adam_step(t, lr, beta1, beta2, eps, weight_decay, step, S(stream)), "adam_step_kernel");
   return kOk;
 }
 

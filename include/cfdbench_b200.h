@@ -131,7 +131,7 @@ size_t fno_rollout_host_scratch_bytes(int batch, int n_case_params, int steps);
 typedef struct fno_train_saved {
   void* act[FNO_MAX_LAYERS + 1]; /* a_0 (lift output) .. a_L (last block output), act_dtype */
   float* pre[FNO_MAX_LAYERS];    /* pre-activation of each block, float32 [B][32][64][64] */
-  void* xm[FNO_MAX_LAYERS];      /* kept modes of a_l, complex64 [B][288][32] */
+  void* xm[FNO_MAX_LAYERS];      /* kept modes of a_l, complex64 [288][B][32] */
 } fno_train_saved;
 
 /* Extra weight views the backward pass needs. */
@@ -179,6 +179,33 @@ int fno_backward(const fno_weights* w, const fno_weights_bwd* wb, const float* i
  * [S][B][64][64]; sums [S][B][3] = (sum (p-l)^2, sum l^2, sum |p-l|) with p, l multiplied by mask. */
 int fno_multistep_metrics(const float* preds_seq, const float* label_u, const float* mask, float* sums, int steps,
                           int batch, void* stream);
+
+/* ---- the rest of a training step (reference src/train_auto.py:233-260) ------------------------------------- */
+
+/* MseLoss.forward (reference src/models/loss.py:22-37) over n = preds.numel() float32 elements, one launch:
+ * out[0..4] = mse, rmse, mae, nmse (= mse / mean(labels^2)), mean(labels^2).  scratch: fno_loss_scratch_bytes()
+ * bytes, zero-initialised once by the caller (the kernel leaves it zeroed).  Deterministic. */
+size_t fno_loss_scratch_bytes(void);
+int fno_loss_fwd(const float* preds, const float* labels, size_t n, void* scratch, float* out, void* stream);
+/* dpreds[i] = d(sum_j gout[j] * out[j]) / dpreds[i], gout = upstream gradients of (mse, rmse, mae, nmse);
+ * `fwd` is the out[] of the matching fno_loss_fwd call. */
+int fno_loss_bwd(const float* preds, const float* labels, const float* fwd, const float* gout, float* dpreds, size_t n,
+                 void* stream);
+
+/* torch.optim.Adam.step (train_auto.py:213,256; no amsgrad, maximize=False) for up to FNO_ADAM_MAX_TENSORS parameter
+ * tensors in ONE launch.  Every array holds float32 views (a complex64 tensor is 2*numel floats, as
+ * torch.view_as_real presents it to Adam); n[i] = number of floats.  `step` is the 1-based step count. */
+#define FNO_ADAM_MAX_TENSORS 32
+typedef struct fno_adam_tensors {
+  int32_t count;
+  void* param[FNO_ADAM_MAX_TENSORS];
+  const void* grad[FNO_ADAM_MAX_TENSORS];
+  void* exp_avg[FNO_ADAM_MAX_TENSORS];
+  void* exp_avg_sq[FNO_ADAM_MAX_TENSORS];
+  int64_t n[FNO_ADAM_MAX_TENSORS];
+} fno_adam_tensors;
+int fno_adam_step(const fno_adam_tensors* t, float lr, float beta1, float beta2, float eps, float weight_decay,
+                  int64_t step, void* stream);
 
 #ifdef __cplusplus
 }

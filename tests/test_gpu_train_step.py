@@ -1,0 +1,114 @@
+"""Native loss (fno_loss_fwd / fno_loss_bwd) and FusedAdam (fno_adam_step) against the torch ops the reference
+uses for the same step (src/models/loss.py:22-37, torch.optim.Adam at src/train_auto.py:213)."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _torch_loss(preds, labels):
+    diff = preds - labels
+    mse = torch.mean(diff * diff)
+    return {"mse": mse, "rmse": torch.sqrt(mse), "mae": torch.mean(torch.abs(diff)),
+            "nmse": mse / torch.mean(labels * labels)}
+
+
+@pytest.mark.parametrize("shape", [(2, 2, 64, 64), (64, 2, 64, 64), (3, 5, 7)])
+def test_native_loss_values_and_gradients(shape):
+    from cfdbench_b200.loss import MseLoss
+    g = torch.Generator().manual_seed(3)
+    preds = torch.randn(shape, generator=g).cuda()
+    labels = (torch.randn(shape, generator=g) * 0.7 + 0.2).cuda()
+    fn = MseLoss(normalize=True)
+    assert fn.get_score_names() == ["mse", "rmse", "mae", "nmse"]
+    for key in ("mse", "rmse", "mae", "nmse"):
+        p1 = preds.clone().requires_grad_(True)
+        p2 = preds.clone().requires_grad_(True)
+        got = fn(preds=p1, labels=labels)
+        ref = _torch_loss(p2.double(), labels.double())
+        assert set(got) == {"mse", "rmse", "mae", "nmse"} and got[key].dim() == 0
+        for k in got:
+            assert abs(got[k].item() - ref[k].item()) <= 2e-6 * abs(ref[k].item()), (k, got[k].item(), ref[k].item())
+        got[key].backward()
+        ref[key].backward()
+        err = (p1.grad.double() - p2.grad).norm() / p2.grad.norm()
+        assert err < 2e-6, (key, err.item())
+    # mixed upstream gradients, repeated calls reuse the scratch buffer (ticket reset), determinism
+    p1 = preds.clone().requires_grad_(True)
+    out = fn(preds=p1, labels=labels)
+    (0.3 * out["mse"] + 2.0 * out["nmse"] - out["mae"]).backward()
+    p2 = preds.clone().double().requires_grad_(True)
+    r = _torch_loss(p2, labels.double())
+    (0.3 * r["mse"] + 2.0 * r["nmse"] - r["mae"]).backward()
+    assert (p1.grad.double() - p2.grad).norm() / p2.grad.norm() < 2e-6
+    a = fn(preds=preds, labels=labels)["nmse"].item()
+    assert all(fn(preds=preds, labels=labels)["nmse"].item() == a for _ in range(3))
+    assert "nmse" not in MseLoss(normalize=False)(preds=preds, labels=labels)
+
+
+@pytest.mark.parametrize("wd", [0.0, 0.01])
+def test_fused_adam_matches_torch_adam(wd):
+    from cfdbench_b200 import FusedAdam
+    g = torch.Generator().manual_seed(5)
+    shapes = [(32, 10, 1, 1), (32,), (32, 32, 12, 12), (128, 32, 1, 1), (2, 128, 1, 1), (5,)]
+    def make():
+        out = []
+        for i, s in enumerate(shapes):
+            if i == 2:
+                t = torch.complex(torch.rand(s, generator=torch.Generator().manual_seed(i)),
+                                  torch.rand(s, generator=torch.Generator().manual_seed(100 + i))) / 1024
+            else:
+                t = torch.randn(s, generator=torch.Generator().manual_seed(i)) * 0.1
+            out.append(torch.nn.Parameter(t.cuda()))
+        return out
+    pa, pb = make(), make()
+    oa = FusedAdam(pa, lr=1e-3, weight_decay=wd)
+    ob = torch.optim.Adam(pb, lr=1e-3, weight_decay=wd)
+    for step in range(4):
+        for i, (a, b) in enumerate(zip(pa, pb)):
+            gr = torch.randn(a.shape, generator=g) * (10.0 ** (-(i % 3)))
+            if a.is_complex():
+                gr = torch.complex(gr, torch.randn(a.shape, generator=g) * 0.01)
+            a.grad = gr.cuda()
+            b.grad = gr.cuda().clone()
+        oa.step()
+        ob.step()
+        for a, b in zip(pa, pb):
+            ra, rb = torch.view_as_real(a.detach()) if a.is_complex() else a.detach(), \
+                torch.view_as_real(b.detach()) if b.is_complex() else b.detach()
+            assert torch.allclose(ra, rb, rtol=2e-6, atol=1e-9), (step, a.shape, (ra - rb).abs().max().item())
+    # optimizer state uses torch's keys / shapes: the stock optimizer can continue from it
+    sd = oa.state_dict()
+    assert set(sd["state"][0]) == {"step", "exp_avg", "exp_avg_sq"}
+    oc = torch.optim.Adam(pa, lr=1e-3, weight_decay=wd)
+    oc.load_state_dict(sd)
+    assert float(oc.state[pa[0]]["step"]) == 4.0
+
+
+def test_training_step_with_native_loss_and_fused_adam_tracks_torch_adam():
+    """Three full steps (fwd -> loss["nmse"].backward() -> step) of two identically initialised models."""
+    from cfdbench_b200 import Fno2d, FusedAdam, synth
+    from cfdbench_b200.loss import loss_name_to_fn
+    p = synth.n_case_params("cavity")
+    sd = synth.make_state_dict(11, n_params=p, spectral_gain=50.0)
+    def model():
+        m = Fno2d(in_chan=2, out_chan=2, n_case_params=p, loss_fn=loss_name_to_fn("nmse"), num_layers=4, hidden_dim=32,
+                  modes1=12, modes2=12).cuda()
+        m.load_state_dict({k: torch.from_numpy(v) for k, v in sd.items()})
+        return m
+    ma, mb = model(), model()
+    oa, ob = FusedAdam(ma.parameters(), lr=1e-4), torch.optim.Adam(mb.parameters(), lr=1e-4)
+    batch = synth.make_batch(2, 4, "cavity")
+    tb = {k: torch.from_numpy(v).cuda() for k, v in batch.items()}
+    for _ in range(3):
+        for m, o in ((ma, oa), (mb, ob)):
+            out = m(**tb)
+            out["loss"]["nmse"].backward()
+            o.step()
+            o.zero_grad()
+    for (n, a), (_, b) in zip(ma.named_parameters(), mb.named_parameters()):
+        ra, rb = (torch.view_as_real(t.detach()) if t.is_complex() else t.detach() for t in (a, b))
+        # Adam's update is lr * m / (sqrt(v) + eps): elements whose gradient is ~0 amplify last-bit differences of the
+        # (atomics-accumulated) small gradients, so compare at 2 % of the 3-step update size (3 * lr = 3e-4)
+        assert torch.allclose(ra, rb, rtol=1e-5, atol=6e-6), (n, (ra - rb).abs().max().item())

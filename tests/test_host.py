@@ -46,6 +46,7 @@ def test_struct_layouts_match_header():
     assert ctypes.sizeof(_lib.FnoGrads) == P * (2 + 4 * 8 + 4)
     assert ctypes.sizeof(_lib.FnoBwdScratch) == 5 * P
     assert ctypes.sizeof(_lib.FnoWeightsBwd) == 16 * P
+    assert ctypes.sizeof(_lib.FnoAdamTensors) == 8 + 32 * (4 * P + 8)
 
 
 def test_size_helpers(built_lib):
