@@ -92,6 +92,7 @@ SIGNATURES = {
     "fno_unpack_spectral_grads": (C.c_int, [_P, _P, _P, _P]),
     "fno_mix_operand_bytes": (C.c_size_t, []),
     "fno_pack_mix_operand": (C.c_int, [_P, _P, _P]),
+    "fno_pack_mix_operand_from_weights": (C.c_int, [_P, _P, _P, _I, _P]),
     "fno_lift_fwd": (C.c_int, [_P, _P, _P, C.POINTER(FnoWeights), _P, _I, _I, _P]),
     "fno_spectral_dft_fwd": (C.c_int, [_P, _P, _I, _I, _F, _F, _P]),
     "fno_mode_mix": (C.c_int, [_P, _P, _P, _I, _P]),

@@ -12,6 +12,7 @@ cudaError_t launch_mode_mix(const void*, const void*, void*, int, cudaStream_t);
 cudaError_t launch_pack_spectral(const void*, const void*, void*, int, cudaStream_t);
 cudaError_t launch_unpack_spectral(const void*, void*, void*, cudaStream_t);
 cudaError_t launch_pack_mix_operand(const void*, void*, cudaStream_t);
+cudaError_t launch_pack_mix_operand_direct(const void*, const void*, void*, int, cudaStream_t);
 size_t mix_operand_bytes();
 cudaError_t launch_loss_fwd(const float*, const float*, size_t, float*, float*, cudaStream_t);
 cudaError_t launch_loss_bwd(const float*, const float*, const float*, const float*, float*, size_t, cudaStream_t);
@@ -85,6 +86,12 @@ size_t fno_mix_operand_bytes(void) { return mix_operand_bytes(); }
 int fno_pack_mix_operand(const void* wk, void* wop, void* stream) {
   if (!wk || !wop) return fail(kErrArg, "fno_pack_mix_operand: null pointer");
   FNO_CUDA(launch_pack_mix_operand(wk, wop, S(stream)), "pack_mix_operand_kernel");
+  return kOk;
+}
+
+int fno_pack_mix_operand_from_weights(const void* w1, const void* w2, void* wop, int conj_transpose, void* stream) {
+  if (!w1 || !w2 || !wop) return fail(kErrArg, "fno_pack_mix_operand_from_weights: null pointer");
+  FNO_CUDA(launch_pack_mix_operand_direct(w1, w2, wop, conj_transpose, S(stream)), "pack_mix_operand_direct_kernel");
   return kOk;
 }
 

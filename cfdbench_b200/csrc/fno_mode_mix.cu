@@ -271,6 +271,49 @@ cudaError_t launch_pack_mix_operand(const void* wk, void* wop, cudaStream_t stre
 
 size_t mix_operand_bytes() { return static_cast<size_t>(kModes) * kMxOperandFloats * sizeof(float); }
 
+// The same image straight from the reference parameter layout (weights1/2: (Cin, Cout, 12, 12) complex64), one
+// launch per layer and direction: a thread produces one 16-byte operand chunk (row n, 4 consecutive kk) of both the
+// hi and the lo image, so the writes are coalesced; the 2.36 MB of weights are gathered through L2.  This is what
+// runs after every optimizer step.
+__global__ void pack_mix_operand_direct_kernel(const float2* __restrict__ w1, const float2* __restrict__ w2,
+                                               float* __restrict__ wop, int conj_transpose) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;  // over k * 1024 + (kk/4) * 64 + n: the operand's own order
+  if (idx >= kModes * 1024) return;
+  const int k = idx >> 10, kq = (idx >> 6) & 15, n = idx & 63;
+  const int kxi = k / kM2, ky = k % kM2;
+  const float2* src = (kxi < kM1) ? w1 : w2;
+  const int kk_mode = (kxi % kM1) * kM2 + ky;
+  const int a = n >> 1, part = n & 1;  // output channel (o) of the mix and its re|im
+  float v[4];
+#pragma unroll
+  for (int j = 0; j < 2; ++j) {
+    const int c = 2 * kq + j;  // input channel (i) of the mix
+    // forward: Wk[k][i = c][o = a] = W[c][a][k];  adjoint: Wk[k][i = c][o = a] = conj(W[a][c][k])
+    const int wi = conj_transpose ? a : c, wo = conj_transpose ? c : a;
+    float2 w = __ldg(src + (static_cast<size_t>(wi) * kC + wo) * (kM1 * kM2) + kk_mode);
+    if (conj_transpose) w.y = -w.y;
+    v[2 * j + 0] = part ? w.y : w.x;    // (o,re): [Wre, -Wim]   (o,im): [Wim, Wre]
+    v[2 * j + 1] = part ? w.x : -w.y;
+  }
+  float4 hi, lo;
+  tc::split_tf32(v[0], hi.x, lo.x);
+  tc::split_tf32(v[1], hi.y, lo.y);
+  tc::split_tf32(v[2], hi.z, lo.z);
+  tc::split_tf32(v[3], hi.w, lo.w);
+  float* img = wop + static_cast<size_t>(k) * kMxOperandFloats;
+  const uint32_t off = tc::kmajor_offset(n, 4 * kq, kMxN) / 4;
+  *reinterpret_cast<float4*>(img + off) = hi;
+  *reinterpret_cast<float4*>(img + kMxBFloats + off) = lo;
+}
+
+cudaError_t launch_pack_mix_operand_direct(const void* w1, const void* w2, void* wop, int conj_transpose,
+                                           cudaStream_t stream) {
+  const int n = kModes * 1024;
+  pack_mix_operand_direct_kernel<<<(n + 255) / 256, 256, 0, stream>>>(
+      static_cast<const float2*>(w1), static_cast<const float2*>(w2), static_cast<float*>(wop), conj_transpose);
+  return cudaGetLastError();
+}
+
 // ------------------------------------------------------------------------------------------------
 // Weight packing: reference parameter layout (Cin, Cout, 12, 12) complex64 x2 (weights1, weights2;
 // reference fno2d.py:31-51)  ->  Wk[k][i][o], k = kxi*12 + ky, kxi<12 from weights1 else weights2.

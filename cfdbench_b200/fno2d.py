@@ -221,14 +221,12 @@ class Fno2d(AutoCfdModel):
         return pk
 
     def _mix_operand(self, blk: "FnoBlock", conj_transpose: int) -> Tensor:
-        """weights1/2 -> packed [288][32][32] complex -> the tensor-core operand image fno_mode_mix consumes."""
+        """weights1/2 -> the tensor-core operand image fno_mode_mix consumes (one launch)."""
         lib = _lib.load()
-        st = self._stream()
-        wk = torch.empty(NMODES, HIDDEN, HIDDEN, dtype=torch.complex64, device=self.device)
-        _lib.check(lib.fno_pack_spectral_weights(blk.conv0.weights1.data_ptr(), blk.conv0.weights2.data_ptr(),
-                                                 wk.data_ptr(), conj_transpose, st), "fno_pack_spectral_weights")
         wop = torch.empty(lib.fno_mix_operand_bytes(), dtype=torch.uint8, device=self.device)
-        _lib.check(lib.fno_pack_mix_operand(wk.data_ptr(), wop.data_ptr(), st), "fno_pack_mix_operand")
+        _lib.check(lib.fno_pack_mix_operand_from_weights(blk.conv0.weights1.data_ptr(), blk.conv0.weights2.data_ptr(),
+                                                         wop.data_ptr(), conj_transpose, self._stream()),
+                   "fno_pack_mix_operand_from_weights")
         return wop
 
     def _workspace(self, batch: int, slot: int = 0):

@@ -80,6 +80,9 @@ int fno_pack_spectral_weights(const void* weights1, const void* weights2, void* 
  * Run once per weight update; for the adjoint mix feed it the conj_transpose=1 pack. */
 size_t fno_mix_operand_bytes(void);
 int fno_pack_mix_operand(const void* wk, void* wop, void* stream);
+/* both steps in one launch: weights1/weights2 -> operand image (what the module runs after every optimizer step) */
+int fno_pack_mix_operand_from_weights(const void* weights1, const void* weights2, void* wop, int conj_transpose,
+                                      void* stream);
 /* gradient wrt packed forward weights [288][32][32] -> gradients of weights1 / weights2 */
 int fno_unpack_spectral_grads(const void* gwk, void* gw1, void* gw2, void* stream);
 

@@ -112,6 +112,16 @@ def test_mode_mix_and_pack_kernels(lib):
     expand[:, 1::2, 1::2] = wkn.real.transpose(0, 2, 1)
     assert np.abs(full.sum(1) - expand).max() <= 2.0 ** -21 * np.abs(expand).max()
     assert np.all((img.view(np.uint32) & 0x1FFF) == 0)  # both images are exact tf32 values
+    # the one-launch pack from the parameter layout produces the same bytes, forward and adjoint
+    wop2 = torch.empty_like(wop)
+    _lib.check(lib.fno_pack_mix_operand_from_weights(w1d.data_ptr(), w2d.data_ptr(), wop2.data_ptr(), 0, stream()), "direct")
+    assert torch.equal(wop, wop2)
+    wkT0 = torch.empty(288, 32, 32, dtype=torch.complex64, device="cuda")
+    _lib.check(lib.fno_pack_spectral_weights(w1d.data_ptr(), w2d.data_ptr(), wkT0.data_ptr(), 1, stream()), "packT")
+    wopT, wopT2 = torch.empty_like(wop), torch.empty_like(wop)
+    _lib.check(lib.fno_pack_mix_operand(wkT0.data_ptr(), wopT.data_ptr(), stream()), "pack operand T")
+    _lib.check(lib.fno_pack_mix_operand_from_weights(w1d.data_ptr(), w2d.data_ptr(), wopT2.data_ptr(), 1, stream()), "direct T")
+    assert torch.equal(wopT, wopT2)
     ym = torch.zeros(288, batch, 32, dtype=torch.complex64, device="cuda")
     _lib.check(lib.fno_mode_mix(xmd.data_ptr(), wop.data_ptr(), ym.data_ptr(), batch, stream()), "mix")
     ref = np.einsum("kbi,iok->kbo", xm.astype(np.complex128), wt)
