@@ -95,6 +95,7 @@ SIGNATURES = {
     "fno_pack_mix_operand_from_weights": (C.c_int, [_P, _P, _P, _I, _P]),
     "fno_lift_fwd": (C.c_int, [_P, _P, _P, C.POINTER(FnoWeights), _P, _I, _I, _P]),
     "fno_spectral_dft_fwd": (C.c_int, [_P, _P, _I, _I, _F, _F, _P]),
+    "fno_spectral_dft_fwd_tc": (C.c_int, [_P, _P, _I, _F, _F, _P]),
     "fno_mode_mix": (C.c_int, [_P, _P, _P, _I, _P]),
     "fno_spectral_inv_kx": (C.c_int, [_P, _P, _I, _F, _F, _P]),
     "fno_block_out": (C.c_int, [_I, _P, _P, _P, _P, _P, _P, _P, _I, _I, _P]),

@@ -11,6 +11,7 @@ cudaError_t launch_dft_fwd(const void*, void*, int, float, float, cudaStream_t);
 cudaError_t launch_mode_mix(const void*, const void*, void*, int, cudaStream_t);
 cudaError_t launch_pack_spectral(const void*, const void*, void*, int, cudaStream_t);
 cudaError_t launch_unpack_spectral(const void*, void*, void*, cudaStream_t);
+cudaError_t launch_dft_fwd_tc(const void*, void*, int, float, float, cudaStream_t);
 cudaError_t launch_pack_mix_operand(const void*, void*, cudaStream_t);
 cudaError_t launch_pack_mix_operand_direct(const void*, const void*, void*, int, cudaStream_t);
 size_t mix_operand_bytes();
@@ -120,6 +121,12 @@ int fno_spectral_dft_fwd(const void* act_in, void* xm, int batch, int act_dtype,
   cudaError_t e = act_dtype == FNO_ACT_F32 ? launch_dft_fwd<float>(act_in, xm, batch, s0, s1, S(stream))
                                            : launch_dft_fwd<__nv_bfloat16>(act_in, xm, batch, s0, s1, S(stream));
   FNO_CUDA(e, "dft_fwd_kernel");
+  return kOk;
+}
+
+int fno_spectral_dft_fwd_tc(const void* act_in_bf16, void* xm, int batch, float s0, float s1, void* stream) {
+  if (!act_in_bf16 || !xm || batch <= 0) return fail(kErrArg, "fno_spectral_dft_fwd_tc: bad argument");
+  FNO_CUDA(launch_dft_fwd_tc(act_in_bf16, xm, batch, s0, s1, S(stream)), "dft_fwd_tc_kernel");
   return kOk;
 }
 

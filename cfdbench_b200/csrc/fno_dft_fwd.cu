@@ -146,13 +146,7 @@ cudaError_t launch_dft_fwd(const void* x, void* xm, int batch, float s0, float s
                         static_cast<float2*>(xm), s0, s1);
 }
 
-// bf16 storage runs the tensor-core kernel (fno_dft_fwd_tc.cu); this file's register-FFT kernel serves fp32 storage
-// and the fp32 gradients of the backward pass.
-cudaError_t launch_dft_fwd_tc(const void* x, void* xm, int batch, float s0, float s1, cudaStream_t stream);
-template <>
-cudaError_t launch_dft_fwd<__nv_bfloat16>(const void* x, void* xm, int batch, float s0, float s1, cudaStream_t stream) {
-  return launch_dft_fwd_tc(x, xm, batch, s0, s1, stream);
-}
 template cudaError_t launch_dft_fwd<float>(const void*, void*, int, float, float, cudaStream_t);
+template cudaError_t launch_dft_fwd<__nv_bfloat16>(const void*, void*, int, float, float, cudaStream_t);
 
 }  // namespace fno
