@@ -104,6 +104,8 @@ SIGNATURES = {
     "fno_forward": (C.c_int, [C.POINTER(FnoWeights), _P, _P, _P, _P, C.POINTER(FnoWorkspace), _I, _I, _P]),
     "fno_rollout": (C.c_int, [C.POINTER(FnoWeights), _P, _P, _P, _P, _I, C.POINTER(FnoWorkspace), _I, _I, _P]),
     "fno_rollout_host": (C.c_int, [C.POINTER(FnoWeights), _P, _P, _P, _P, _I, C.POINTER(FnoWorkspace), _P, _I, _I, _P]),
+    "fno_rollout_host_chunked": (C.c_int, [C.POINTER(FnoWeights), _P, _P, _P, _P, C.POINTER(FnoWorkspace),
+                                           C.POINTER(C.c_void_p), _I, _I, _I, _P, _P, _P]),
     "fno_rollout_host_scratch_bytes": (C.c_size_t, [_I, _I, _I]),
     "fno_multistep_metrics": (C.c_int, [_P, _P, _P, _P, _I, _I, _P]),
     "fno_loss_scratch_bytes": (C.c_size_t, []),

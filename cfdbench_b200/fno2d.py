@@ -150,7 +150,7 @@ class Fno2d(AutoCfdModel):
         # every kernel on the stream.
         self.graph_rollout = True
         self.max_graphs = 8
-        self.host_chunks = 4  # batch chunks (streams) of the host-tensor rollout path
+        self.host_chunks = 2  # batch chunks of the pipelined host-tensor rollout path (upload | kernels | download)
         self._graphs: dict = {}
 
     # ------------------------------------------------------------------------------------ plumbing
@@ -445,9 +445,11 @@ class Fno2d(AutoCfdModel):
         return seq
 
     def _rollout_host(self, inputs: Tensor, case_params: Tensor, mask: Tensor, steps: int) -> Tensor:
-        """Host tensors in -> host tensors out.  Each batch chunk runs `fno_rollout_host` (H2D, rollout, D2H) on its
-        own stream; with several chunks the copies of one chunk overlap the kernels of another (the cases are
-        independent), which is what bounds the per-step host round trip of `bench.py`'s e2e number."""
+        """Host tensors in -> host tensors out.  Multi-step rollouts run `fno_rollout_host` (H2D, rollout, D2H on one
+        stream).  A single step of a large batch runs `fno_rollout_host_chunked`: the batch is cut into chunks whose
+        uploads, kernels and downloads go through three streams chained by events, so the copies of one chunk overlap
+        the kernels of another (the cases are independent) -- this bounds the per-step host round trip of `bench.py`'s
+        e2e number."""
         lib = _lib.load()
         b = inputs.shape[0]
         if tuple(inputs.shape[1:]) != (self.in_chan, H, W):
@@ -467,7 +469,7 @@ class Fno2d(AutoCfdModel):
                 dev_io=[torch.empty(nbytes, dtype=torch.uint8, device=self.device) for _ in range(n_chunks)],
                 # two pinned result buffers used alternately: the previous result stays valid for one more call
                 out=[torch.empty(steps, b, self.out_chan, H, W, dtype=torch.float32).pin_memory() for _ in range(2)],
-                streams=[torch.cuda.Stream(device=self.device) for _ in range(n_chunks)] if n_chunks > 1 else [],
+                streams=[torch.cuda.Stream(device=self.device) for _ in range(3)] if n_chunks > 1 else [],
                 flip=0,
             )
             self._ws_cache[key] = ent
@@ -481,16 +483,16 @@ class Fno2d(AutoCfdModel):
                                             ent["dev_io"][0].data_ptr(), b, self._act_code(), self._stream()),
                        "fno_rollout_host")
         else:
-            for c, st in enumerate(ent["streams"]):
-                st.wait_stream(cur)  # weight packing etc. happened on the current stream
-                ws, _ = self._workspace(cb, slot=1 + c)
-                lo = c * cb
-                _lib.check(lib.fno_rollout_host(C.byref(pk["struct"]), inputs[lo:lo + cb].data_ptr(),
-                                                mask3[lo:lo + cb].data_ptr(), case_params[lo:lo + cb].data_ptr(),
-                                                out[0, lo:lo + cb].data_ptr(), 1, C.byref(ws),
-                                                ent["dev_io"][c].data_ptr(), cb, self._act_code(),
-                                                C.c_void_p(st.cuda_stream)), "fno_rollout_host")
+            s_in, s_cmp, s_out = ent["streams"]
             for st in ent["streams"]:
-                cur.wait_stream(st)
+                st.wait_stream(cur)  # weight packing etc. happened on the current stream
+            ws_arr = (_lib.FnoWorkspace * n_chunks)(*[self._workspace(cb, slot=1 + c)[0] for c in range(n_chunks)])
+            io_arr = (C.c_void_p * n_chunks)(*[ent["dev_io"][c].data_ptr() for c in range(n_chunks)])
+            _lib.check(lib.fno_rollout_host_chunked(C.byref(pk["struct"]), inputs.data_ptr(), mask3.data_ptr(),
+                                                    case_params.data_ptr(), out.data_ptr(), ws_arr, io_arr, b, n_chunks,
+                                                    self._act_code(), C.c_void_p(s_in.cuda_stream),
+                                                    C.c_void_p(s_cmp.cuda_stream), C.c_void_p(s_out.cuda_stream)),
+                       "fno_rollout_host_chunked")
+            cur.wait_stream(s_out)
         cur.synchronize()
         return out

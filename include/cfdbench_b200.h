@@ -128,6 +128,15 @@ int fno_rollout(const fno_weights* w, const float* inputs, const float* mask, co
 int fno_rollout_host(const fno_weights* w, const float* inputs_host, const float* mask_host,
                      const float* case_params_host, float* preds_seq_host, int steps, const fno_workspace* ws,
                      void* dev_io, int batch, int act_dtype, void* stream);
+/* One step (steps = 1) for host buffers, pipelined over n_chunks equal batch chunks: uploads, kernels and downloads
+ * run on three caller-provided streams chained by events, so chunk c+1's upload overlaps chunk c's kernels and
+ * chunk c-1's download while copies of one direction stay serialised.  ws_chunks / dev_io_chunks: one workspace and
+ * one fno_rollout_host_scratch_bytes(batch / n_chunks, p, 1) buffer per chunk.  The caller orders the three streams
+ * after its own stream before the call and waits for stream_out afterwards. */
+int fno_rollout_host_chunked(const fno_weights* w, const float* inputs_host, const float* mask_host,
+                             const float* case_params_host, float* preds_host, const fno_workspace* ws_chunks,
+                             void* const* dev_io_chunks, int batch, int n_chunks, int act_dtype, void* stream_in,
+                             void* stream_compute, void* stream_out);
 size_t fno_rollout_host_scratch_bytes(int batch, int n_case_params, int steps);
 
 /* ---------------------------------------------------------------------------------------------------
