@@ -38,7 +38,7 @@ sys.path.insert(0, ROOT)
 from cfdbench_b200 import dp, synth  # noqa: E402
 
 # dram__bytes_read.sum + dram__bytes_write.sum of one block_tc_kernel launch at B=256 from the `ncu --set full`
-# capture summarised in profiles/ncu_r01h.md (bf16 storage: 117.6 MB read + 35.8 MB written; the read side
+# capture summarised in profiles/ncu_r01j.md (bf16 storage: 117.6 MB read + 35.8 MB written; the read side
 # includes the fp32 Z rows produced by inv_kx_kernel that are not part of the algorithmic byte count, and part of
 # the output is still in L2 when the kernel ends).
 NCU_TRAFFIC_BYTES = {("bf16", 256): 153320960}
