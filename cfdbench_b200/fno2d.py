@@ -145,7 +145,7 @@ class Fno2d(AutoCfdModel):
         self._ws_cache: dict = {}
         self._dp_group = None
         self._dp_enabled = False
-        # CUDA-graph replay of device-resident rollouts: one capture per (batch, steps), the 22 launches of every
+        # CUDA-graph replay of device-resident rollouts: one capture per (batch, steps), the 18 launches of every
         # step replayed as one graph (B=256: 591 -> 544 us/step, B=1: 2.09 -> 1.48 ms per 20 steps).  False = launch
         # every kernel on the stream.
         self.graph_rollout = True
