@@ -8,7 +8,7 @@ Public surface mirrors the reference's for this path:
 from .base_model import AutoCfdModel
 from .loss import MseLoss, loss_name_to_fn
 
-__all__ = ["AutoCfdModel", "MseLoss", "loss_name_to_fn", "Fno2d", "FnoBlock", "SpectralConv2d_fast", "FusedAdam"]
+__all__ = ["AutoCfdModel", "MseLoss", "loss_name_to_fn", "Fno2d", "FnoBlock", "SpectralConv2d_fast", "FusedAdam", "DeviceFrames"]
 
 
 def __getattr__(name):  # lazy: importing the package must not require the native library
@@ -18,4 +18,7 @@ def __getattr__(name):  # lazy: importing the package must not require the nativ
     if name == "FusedAdam":
         from .optim import FusedAdam
         return FusedAdam
+    if name == "DeviceFrames":
+        from .data import DeviceFrames
+        return DeviceFrames
     raise AttributeError(name)

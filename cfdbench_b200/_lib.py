@@ -108,6 +108,7 @@ SIGNATURES = {
                                            C.POINTER(C.c_void_p), _I, _I, _I, _P, _P, _P]),
     "fno_rollout_host_scratch_bytes": (C.c_size_t, [_I, _I, _I]),
     "fno_multistep_metrics": (C.c_int, [_P, _P, _P, _P, _I, _I, _P]),
+    "fno_gather_batch": (C.c_int, [_P, _P, _P, _P, _P, _I, _I, _I, _P, _P, _P, _P, _P]),
     "fno_loss_scratch_bytes": (C.c_size_t, []),
     "fno_loss_fwd": (C.c_int, [_P, _P, C.c_size_t, _P, _P, _P]),
     "fno_loss_bwd": (C.c_int, [_P, _P, _P, _P, _P, C.c_size_t, _P]),

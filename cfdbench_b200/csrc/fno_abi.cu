@@ -15,6 +15,8 @@ cudaError_t launch_dft_fwd_tc(const void*, void*, int, float, float, cudaStream_
 cudaError_t launch_pack_mix_operand(const void*, void*, cudaStream_t);
 cudaError_t launch_pack_mix_operand_direct(const void*, const void*, void*, int, cudaStream_t);
 size_t mix_operand_bytes();
+cudaError_t launch_gather_batch(const void*, const void*, const float*, const int*, const long long*, int, int, int, float*,
+                                float*, float*, float*, cudaStream_t);
 cudaError_t launch_loss_fwd(const float*, const float*, size_t, float*, float*, cudaStream_t);
 cudaError_t launch_loss_bwd(const float*, const float*, const float*, const float*, float*, size_t, cudaStream_t);
 size_t loss_scratch_bytes();
@@ -374,6 +376,19 @@ int fno_multistep_metrics(const float* preds_seq, const float* label_u, const fl
   if (!preds_seq || !label_u || !mask || !sums || steps <= 0 || batch <= 0)
     return fail(kErrArg, "fno_multistep_metrics: bad argument");
   FNO_CUDA(launch_multistep_metrics(preds_seq, label_u, mask, sums, steps, batch, S(stream)), "multistep_metrics_kernel");
+  return kOk;
+}
+
+int fno_gather_batch(const void* frames_in, const void* frames_out, const float* case_table, const int32_t* case_ids,
+                     const int64_t* idx, int n_idx, int n_case_params, int frame_dtype, float* inputs, float* label,
+                     float* mask, float* case_params, void* stream) {
+  if (!frames_in || !frames_out || !case_ids || !idx || !inputs || !label || !mask || n_idx <= 0 || n_case_params < 0 ||
+      n_case_params > kMaxCaseParams || bad_dtype(frame_dtype) || (n_case_params > 0 && (!case_table || !case_params)))
+    return fail(kErrArg, "fno_gather_batch: bad argument");
+  FNO_CUDA(launch_gather_batch(frames_in, frames_out, case_table, reinterpret_cast<const int*>(case_ids),
+                               reinterpret_cast<const long long*>(idx), n_idx, n_case_params, frame_dtype == FNO_ACT_BF16,
+                               inputs, label, mask, case_params, S(stream)),
+           "gather_batch_kernel");
   return kOk;
 }
 

@@ -196,6 +196,15 @@ int fno_backward(const fno_weights* w, const fno_weights_bwd* wb, const float* i
 int fno_multistep_metrics(const float* preds_seq, const float* label_u, const float* mask, float* sums, int steps,
                           int batch, void* stream);
 
+/* one training batch gathered on the device from resident frames -- replaces DataLoader indexing +
+ * collate_fn (reference src/train_auto.py:33-58: stack, channel slices, case-parameter dict loop, four .cuda() copies).
+ * frames_in / frames_out: [N][3][64][64] (u, v, mask) as the dataset holds them (src/dataset/cavity.py:326-331), float32
+ * (frame_dtype = FNO_ACT_F32) or bfloat16 (FNO_ACT_BF16); case_table [n_cases][p]; case_ids [N] int32; idx [n_idx] int64.
+ * Outputs (float32): inputs [n][2][64][64], label [n][2][64][64], mask [n][1][64][64], case_params [n][p]. */
+int fno_gather_batch(const void* frames_in, const void* frames_out, const float* case_table, const int32_t* case_ids,
+                     const int64_t* idx, int n_idx, int n_case_params, int frame_dtype, float* inputs, float* label,
+                     float* mask, float* case_params, void* stream);
+
 /* ---- the rest of a training step (reference src/train_auto.py:233-260) ------------------------------------- */
 
 /* MseLoss.forward (reference src/models/loss.py:22-37) over n = preds.numel() float32 elements, one launch:
