@@ -31,13 +31,15 @@ class _NativeLoss(torch.autograd.Function):
         if p.shape != l.shape:
             raise ValueError(f"preds {tuple(p.shape)} and labels {tuple(l.shape)} differ")
         dev = p.device
-        scratch = _NativeLoss._scratch.get(dev)
-        if scratch is None:
-            scratch = torch.zeros(lib.fno_loss_scratch_bytes(), dtype=torch.uint8, device=dev)
-            _NativeLoss._scratch[dev] = scratch
         out = torch.empty(5, dtype=torch.float32, device=dev)
         with torch.cuda.device(dev):
-            st = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+            stream = torch.cuda.current_stream(dev)
+            key = (dev, stream.cuda_stream)  # the partial-sum table is reused call after call: one per stream
+            scratch = _NativeLoss._scratch.get(key)
+            if scratch is None:
+                scratch = torch.zeros(lib.fno_loss_scratch_bytes(), dtype=torch.uint8, device=dev)
+                _NativeLoss._scratch[key] = scratch
+            st = C.c_void_p(stream.cuda_stream)
             _lib.check(lib.fno_loss_fwd(p.data_ptr(), l.data_ptr(), p.numel(), scratch.data_ptr(), out.data_ptr(), st),
                        "fno_loss_fwd")
         ctx.save_for_backward(p, l, out)
