@@ -71,8 +71,6 @@ constexpr uint32_t kLboA = (kBtM / 8) * 128;  // 2048
 constexpr uint32_t kLboB = (kC / 8) * 128;    // 512
 constexpr int kBtTilesPerSample = kHW / kBtM;  // 32
 constexpr int kETabFloats = 2 * kBtM * kKE;
-constexpr int kBtTmemE = 64;          // warp-specialised kernel: TMEM columns [0,64) accumulators, [64,160) E hi, E lo
-constexpr int kBtTmemCols = 256;
 // Operand staging is done by warps 1..7 of a pipeline only: warp 0 issues the tile's ~30 MMAs in that time, so all
 // eight warps reach the group barrier together.
 constexpr int kBtWorkers = kBtGroup - 32;
@@ -96,12 +94,10 @@ struct BtSmem {
   uint32_t tmem_base;
 };
 
-template <typename TAct, int NW = kBtWorkers>
+template <typename TAct>
 struct BtRegs {
-  static constexpr int kXReps = (kBtXTasks + NW - 1) / NW;
-  static_assert(2 * NW >= kBtZTasks, "two z reps must cover the tile");
-  TAct x[kXReps][4];  // task = rep*NW + wtid (< 1024) -> (pixel m = task & 127, channel quad = task >> 7)
-  float z[2][4];      // task = rep*NW + wtid (< 384)  -> (o = task & 31, k quad = task >> 5)
+  TAct x[kBtXReps][4];  // task = rep*224 + wtid (< 1024) -> (pixel m = task & 127, channel quad = task >> 7)
+  float z[2][4];        // task = rep*224 + wtid (< 384)  -> (o = task & 31, k quad = task >> 5)
 };
 
 __device__ __forceinline__ float bt_to_float(float v) { return v; }
@@ -109,14 +105,14 @@ __device__ __forceinline__ float bt_to_float(__nv_bfloat16 v) { return __bfloat1
 __device__ __forceinline__ void bt_store(float* p, float v) { *p = v; }
 __device__ __forceinline__ void bt_store(__nv_bfloat16* p, float v) { *p = __float2bfloat16_rn(v); }
 
-template <typename TAct, int NW = kBtWorkers>
-__device__ __forceinline__ void bt_prefetch(BtRegs<TAct, NW>& r, const TAct* __restrict__ x, const float* __restrict__ z,
+template <typename TAct>
+__device__ __forceinline__ void bt_prefetch(BtRegs<TAct>& r, const TAct* __restrict__ x, const float* __restrict__ z,
                                             int tile, int wtid) {
   if (wtid < 0) return;
   const int b = tile / kBtTilesPerSample, tt = tile % kBtTilesPerSample;
 #pragma unroll
-  for (int rep = 0; rep < BtRegs<TAct, NW>::kXReps; ++rep) {
-    const int task = rep * NW + wtid;
+  for (int rep = 0; rep < kBtXReps; ++rep) {
+    const int task = rep * kBtWorkers + wtid;
     if (task < kBtXTasks) {
       const int m = task & (kBtM - 1), kq = task >> 7;
       const TAct* src = x + (static_cast<size_t>(b) * kC + 4 * kq) * kHW + tt * kBtM + m;
@@ -126,7 +122,7 @@ __device__ __forceinline__ void bt_prefetch(BtRegs<TAct, NW>& r, const TAct* __r
   }
 #pragma unroll
   for (int rep = 0; rep < 2; ++rep) {
-    const int task = rep * NW + wtid;
+    const int task = rep * kBtWorkers + wtid;
     if (task < kBtZTasks) {
       const int o = task & 31, kq = task >> 5;           // kq 0..11: row j = kq / 6, column quad (kq % 6)
       const int j = kq / 6, kk0 = (kq % 6) * 4;
@@ -137,13 +133,13 @@ __device__ __forceinline__ void bt_prefetch(BtRegs<TAct, NW>& r, const TAct* __r
   }
 }
 
-template <typename TAct, int NW = kBtWorkers>
-__device__ __forceinline__ void bt_split_store(const BtRegs<TAct, NW>& r, float* ax_hi, float* ax_lo, float* bz_hi,
+template <typename TAct>
+__device__ __forceinline__ void bt_split_store(const BtRegs<TAct>& r, float* ax_hi, float* ax_lo, float* bz_hi,
                                                float* bz_lo, const float* bias_s, int wtid) {
   if (wtid < 0) return;
 #pragma unroll
-  for (int rep = 0; rep < BtRegs<TAct, NW>::kXReps; ++rep) {
-    const int task = rep * NW + wtid;
+  for (int rep = 0; rep < kBtXReps; ++rep) {
+    const int task = rep * kBtWorkers + wtid;
     if (task < kBtXTasks) {
       const int m = task & (kBtM - 1), kq = task >> 7;
       float hi[4], lo[4];
@@ -160,7 +156,7 @@ __device__ __forceinline__ void bt_split_store(const BtRegs<TAct, NW>& r, float*
   }
 #pragma unroll
   for (int rep = 0; rep < 2; ++rep) {
-    const int task = rep * NW + wtid;
+    const int task = rep * kBtWorkers + wtid;
     if (task < kBtZTasks) {
       const int o = task & 31, kq = task >> 5;
       float hi[4], lo[4];
@@ -339,203 +335,6 @@ __global__ void __launch_bounds__(kBtThreads, 1)
   if (warp == 0) tc::tmem_dealloc<4 * kC>(sm.tmem_base);
 }
 
-// ------------------------------------------------------------------------------------------------ K3b, warp-specialised
-// Same tile and the same MMA chain as block_tc_kernel, but the three phases of a tile run in different warps and
-// overlap across tiles instead of adding up inside one pipeline (profiles/README.md: 12 us fixed + 10 us of per-tile
-// synchronisation + four serial work phases):
-//   warp 0        issues the MMAs.  The constant E operand lives in TENSOR MEMORY (22.7 instead of 45.6 cycles per
-//                 MMA, tools/tc_probe3.cu), so a tile costs ~0.8k issue cycles.
-//   warps 1..11   producers: global -> registers (two tiles in flight) -> tf32 split -> operand ring in shared memory.
-//   warps 12..15  epilogue: one warp per TMEM lane quadrant, alternating over the two accumulators.
-// Hand-offs are mbarriers: full[s] (11 producer warps arrive) / empty[s] (tcgen05.commit) for the operand ring,
-// acc_full[b] (tcgen05.commit) / acc_empty[b] (the 4 epilogue warps arrive) for the accumulators.
-constexpr int kWsThreads = 512;
-constexpr int kWsProducerWarps = 11;                 // warps 1..11
-constexpr int kWsWorkers = kWsProducerWarps * 32;    // 352 staging threads
-
-template <typename TAct>
-struct WsSmem {
-  static constexpr int kStages = sizeof(TAct) == 2 ? 4 : 3;
-  alignas(128) float ax_hi[kStages][kBtM * kKConv];                          // 16 KB per stage
-  alignas(128) float ax_lo[sizeof(TAct) == 2 ? 1 : kStages][kBtM * kKConv];  // fp32 storage only
-  alignas(128) float bz_hi[kStages][kC * kKE];                               // 6 KB per stage
-  alignas(128) float bz_lo[kStages][kC * kKE];
-  alignas(128) float wb_hi[kC * kKConv];
-  alignas(128) float wb_lo[kC * kKConv];
-  alignas(16) float bias[kC];
-  alignas(8) uint64_t full_bar[kStages];
-  alignas(8) uint64_t empty_bar[kStages];
-  alignas(8) uint64_t acc_full_bar[2];
-  alignas(8) uint64_t acc_empty_bar[2];
-  uint32_t tmem_base;
-};
-
-template <typename TAct, int EPI>
-__global__ void __launch_bounds__(kWsThreads, 1)
-    block_ws_kernel(const float* __restrict__ z, const TAct* __restrict__ x, const float* __restrict__ w0t,
-                    const float* __restrict__ bias, const float* __restrict__ etab_rm, TAct* __restrict__ out,
-                    float* __restrict__ pre_out, const float* __restrict__ pre_in, int n_tiles) {
-  using Smem = WsSmem<TAct>;
-  constexpr int S = Smem::kStages;
-  constexpr bool kBf16 = sizeof(TAct) == 2;
-  extern __shared__ __align__(1024) unsigned char smem_raw[];
-  Smem& sm = *reinterpret_cast<Smem*>(smem_raw);
-  if ((smem_u32(smem_raw) & 127u) != 0) __trap();
-  const int tid = threadIdx.x, lane = tid & 31, warp = tc::warp_index_uniform();
-
-  if (tid == 0) {
-#pragma unroll
-    for (int s = 0; s < S; ++s) {
-      mbar_init(&sm.full_bar[s], kWsProducerWarps);
-      mbar_init(&sm.empty_bar[s], 1);
-    }
-#pragma unroll
-    for (int b = 0; b < 2; ++b) {
-      mbar_init(&sm.acc_full_bar[b], 1);
-      mbar_init(&sm.acc_empty_bar[b], 4);
-    }
-    fence_mbar_init();
-  }
-  if (warp == 0) tc::tmem_alloc<kBtTmemCols>(&sm.tmem_base);
-  for (int e = tid; e < kC * kKConv; e += kWsThreads) {  // B[n = o][k = i] = W0[o][i] = w0t[i][o]
-    const int i = e / kC, o = e % kC;
-    float hi, lo;
-    tc::split_tf32(w0t[e], hi, lo);
-    const uint32_t off = tc::kmajor_offset(o, i, kC) / 4;
-    sm.wb_hi[off] = hi;
-    sm.wb_lo[off] = lo;
-  }
-  constexpr bool kHasBias = EPI == kEpiGelu || EPI == kEpiGeluSavePre;
-  if (tid < kC) sm.bias[tid] = (kHasBias && bias != nullptr) ? bias[tid] : 0.f;
-  tc::fence_proxy_async_smem();
-  tc::fence_before_thread_sync();
-  __syncthreads();
-  tc::fence_after_thread_sync();
-  const uint32_t tmem_acc = sm.tmem_base;             // [buffer] x 32 columns
-  const uint32_t tmem_e = sm.tmem_base + kBtTmemE;    // E hi (48 columns), E lo (48 columns)
-  if (warp >= 8) {  // constant E operand -> tensor memory: warps 8..11 the hi image, 12..15 the lo image
-    const int m = (warp & 3) * 32 + lane, img = (warp - 8) >> 2;  // (lane quadrant = warp & 3)
-    const float* src = etab_rm + (static_cast<size_t>(img) * kBtM + m) * kKE;
-    const uint32_t taddr = tmem_e + img * kKE + (static_cast<uint32_t>((warp & 3) * 32) << 16);
-#pragma unroll
-    for (int c0 = 0; c0 < kKE; c0 += 16) {
-      float v[16];
-#pragma unroll
-      for (int c = 0; c < 16; c += 4) {
-        const float4 q = __ldg(reinterpret_cast<const float4*>(src + c0 + c));
-        v[c] = q.x; v[c + 1] = q.y; v[c + 2] = q.z; v[c + 3] = q.w;
-      }
-      tc::tmem_st16(taddr + c0, v);
-    }
-    tc::tmem_wait_st();
-  }
-  tc::fence_before_thread_sync();
-  __syncthreads();
-  tc::fence_after_thread_sync();
-  pdl_wait();  // everything above touched only weights / the constant E table; z and x come from the chain
-  pdl_launch_dependents();
-
-  const int first = blockIdx.x, stride = gridDim.x;
-  const int n_mine = (first < n_tiles) ? (n_tiles - first + stride - 1) / stride : 0;
-  auto tile_of = [&](int i) { return first + i * stride; };
-
-  if (warp == 0) {
-    // ------------------------------------------------------------------------------------------ MMA warp
-    constexpr uint32_t idesc = tc::make_idesc_tf32(kBtM, kC);
-    for (int i = 0; i < n_mine; ++i) {
-      const int s = i % S, b = i & 1;
-      mbar_wait(&sm.full_bar[s], (i / S) & 1);
-      if (i >= 2) mbar_wait(&sm.acc_empty_bar[b], ((i >> 1) - 1) & 1);
-      tc::fence_after_thread_sync();
-      if (tc::elect_one()) {
-        const uint32_t d_tmem = tmem_acc + b * kC;
-        const uint32_t a_e[3] = {tmem_e, tmem_e + kKE, tmem_e};
-        const uint32_t zh = tc::smem_addr(sm.bz_hi[0]) + s * sizeof(sm.bz_hi[0]);
-        const uint32_t zl = tc::smem_addr(sm.bz_lo[0]) + s * sizeof(sm.bz_lo[0]);
-        const uint32_t xh = tc::smem_addr(sm.ax_hi[0]) + s * sizeof(sm.ax_hi[0]);
-        const uint32_t xl = kBf16 ? xh : tc::smem_addr(sm.ax_lo[0]) + s * sizeof(sm.ax_lo[0]);
-        const uint32_t b_z[3] = {zh, zh, zl};
-        const uint32_t a_x[3] = {xh, xl, xh};
-        const uint32_t b_w[3] = {tc::smem_addr(sm.wb_hi), tc::smem_addr(sm.wb_hi), tc::smem_addr(sm.wb_lo)};
-#pragma unroll
-        for (int pass = 0; pass < 3; ++pass) {
-          const uint64_t db0 = tc::make_smem_desc(b_z[pass], kLboB, 128);
-#pragma unroll
-          for (int ks = 0; ks < kKE / 8; ++ks) {
-            const uint64_t db = db0 + ((ks * 2 * kLboB) >> 4);
-            if (pass == 0 && ks == 0) tc::mma_tf32_tmem_a_imm<false>(d_tmem, a_e[pass] + ks * 8, db, idesc);
-            else tc::mma_tf32_tmem_a_imm<true>(d_tmem, a_e[pass] + ks * 8, db, idesc);
-          }
-          if (kBf16 && pass == 1) continue;  // conv-part A has no lo component
-          const uint64_t dx0 = tc::make_smem_desc(a_x[pass], kLboA, 128);
-          const uint64_t dw0 = tc::make_smem_desc(b_w[pass], kLboB, 128);
-#pragma unroll
-          for (int ks = 0; ks < kKConv / 8; ++ks)
-            tc::mma_tf32_imm<true>(d_tmem, dx0 + ((ks * 2 * kLboA) >> 4), dw0 + ((ks * 2 * kLboB) >> 4), idesc);
-        }
-        tc::mma_commit(&sm.empty_bar[s]);      // the operands of stage s have been consumed
-        tc::mma_commit(&sm.acc_full_bar[b]);   // the accumulator of this tile is complete
-      }
-      __syncwarp();
-    }
-  } else if (warp <= kWsProducerWarps) {
-    // ------------------------------------------------------------------------------------------ producers
-    const int wtid = tid - 32;
-    BtRegs<TAct, kWsWorkers> ring[2];
-    if (n_mine > 0) bt_prefetch<TAct, kWsWorkers>(ring[0], x, z, tile_of(0), wtid);
-    if (n_mine > 1) bt_prefetch<TAct, kWsWorkers>(ring[1], x, z, tile_of(1), wtid);
-    auto produce = [&](int i, BtRegs<TAct, kWsWorkers>& regs) {
-      const int s = i % S;
-      if (i >= S) mbar_wait(&sm.empty_bar[s], ((i / S) - 1) & 1);  // the MMAs of tile i - S are done with stage s
-      bt_split_store<TAct, kWsWorkers>(regs, sm.ax_hi[s], sm.ax_lo[kBf16 ? 0 : s], sm.bz_hi[s], sm.bz_lo[s], sm.bias, wtid);
-      tc::fence_proxy_async_smem();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&sm.full_bar[s]);
-      if (i + 2 < n_mine) bt_prefetch<TAct, kWsWorkers>(regs, x, z, tile_of(i + 2), wtid);
-    };
-    for (int i = 0; i < n_mine; i += 2) {
-      produce(i, ring[0]);
-      if (i + 1 < n_mine) produce(i + 1, ring[1]);
-    }
-  } else {
-    // ------------------------------------------------------------------------------------------ epilogue warps
-    const int quad = warp & 3;
-    for (int i = 0; i < n_mine; ++i) {
-      const int set = i & 1;
-      mbar_wait(&sm.acc_full_bar[set], (i >> 1) & 1);
-      tc::fence_after_thread_sync();
-      float v[32];
-      tc::tmem_ld32(tmem_acc + set * kC + (static_cast<uint32_t>(quad * 32) << 16), v);
-      tc::fence_before_thread_sync();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&sm.acc_empty_bar[set]);  // the accumulator may be overwritten
-      const int tile = tile_of(i);
-      const int b = tile / kBtTilesPerSample, pix = (tile % kBtTilesPerSample) * kBtM + quad * 32 + lane;
-      const size_t base = static_cast<size_t>(b) * kC * kHW + pix;
-#pragma unroll
-      for (int c = 0; c < kC; c += 2) {
-        float2 p = make_float2(v[c], v[c + 1]);
-        const size_t o0 = base + static_cast<size_t>(c) * kHW, o1 = o0 + kHW;
-        if constexpr (EPI == kEpiGelu || EPI == kEpiGeluSavePre) {  // the accumulator already includes the bias
-          if constexpr (EPI == kEpiGeluSavePre) {
-            pre_out[o0] = p.x;
-            pre_out[o1] = p.y;
-          }
-          p = gelu_erf2(p);
-        } else if constexpr (EPI == kEpiMulDgelu) {
-          p.x *= dgelu_erf(__ldg(pre_in + o0));
-          p.y *= dgelu_erf(__ldg(pre_in + o1));
-        }
-        bt_store(out + o0, p.x);
-        bt_store(out + o1, p.y);
-      }
-    }
-  }
-  tc::fence_before_thread_sync();
-  __syncthreads();
-  if (warp == 0) tc::tmem_dealloc<kBtTmemCols>(sm.tmem_base);
-}
-
 // ------------------------------------------------------------------------------------------------
 // Constant A-operand image of the C2R stage: rows m = 64 j + w (j = row of the tile), columns
 // k = 24 j' + 2 ky + ri;  E = cos(2 pi ky w/64) (ri=0), -sin(2 pi ky w/64) (ri=1), zero for j != j'.  The
@@ -560,8 +359,8 @@ static cudaError_t ensure_etab(const float** out, cudaStream_t stream) {
   if (e != cudaSuccess) return e;
   if (dev < 0 || dev >= 64) return cudaErrorInvalidDevice;
   if (g_etab[dev] == nullptr) {
-    static float host[2 * kETabFloats];  // K-major UMMA image (block_tc_kernel), then row-major [image][m][k] (block_ws_kernel)
-    for (int i = 0; i < 2 * kETabFloats; ++i) host[i] = 0.f;
+    static float host[kETabFloats];
+    for (int i = 0; i < kETabFloats; ++i) host[i] = 0.f;
     for (int m = 0; m < kBtM; ++m) {
       const int j = m >> 6, w = m & 63;
       for (int ky = 0; ky < kM2; ++ky) {
@@ -574,8 +373,6 @@ static cudaError_t ensure_etab(const float** out, cudaStream_t stream) {
           const uint32_t off = tc::kmajor_offset(m, k, kBtM) / 4;
           host[off] = hi;
           host[kBtM * kKE + off] = lo;
-          host[kETabFloats + m * kKE + k] = hi;
-          host[kETabFloats + kBtM * kKE + m * kKE + k] = lo;
         }
       }
     }
@@ -592,38 +389,9 @@ static cudaError_t ensure_etab(const float** out, cudaStream_t stream) {
   return cudaSuccess;
 }
 
-constexpr bool kUseWarpSpecialised = true;
-
-template <typename TAct, int EPI>
-static cudaError_t launch_one_ws(const void* z, const void* x, const float* w0t, const float* bias, void* out,
-                                 float* pre_out, const float* pre_in, int batch, cudaStream_t stream) {
-  auto kern = block_ws_kernel<TAct, EPI>;
-  constexpr size_t smem = sizeof(WsSmem<TAct>);
-  static bool configured = false;
-  static int n_sm = 0;
-  if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    int dev = 0;
-    cudaGetDevice(&dev);
-    e = cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
-    if (e != cudaSuccess) return e;
-    configured = true;
-  }
-  const float* etab = nullptr;
-  cudaError_t e = ensure_etab(&etab, stream);
-  if (e != cudaSuccess) return e;
-  const int n_tiles = batch * kBtTilesPerSample;
-  const int grid = n_tiles < n_sm ? n_tiles : n_sm;
-  return launch_chained(kern, dim3(grid), dim3(kWsThreads), smem, stream, static_cast<const float*>(z),
-                        static_cast<const TAct*>(x), w0t, bias, etab + kETabFloats, static_cast<TAct*>(out), pre_out, pre_in,
-                        n_tiles);
-}
-
 template <typename TAct, int EPI>
 static cudaError_t launch_one(const void* z, const void* x, const float* w0t, const float* bias, void* out,
                               float* pre_out, const float* pre_in, int batch, cudaStream_t stream) {
-  if (kUseWarpSpecialised) return launch_one_ws<TAct, EPI>(z, x, w0t, bias, out, pre_out, pre_in, batch, stream);
   auto kern = block_tc_kernel<TAct, EPI>;
   constexpr size_t smem = sizeof(BtSmem);
   static bool configured = false;
