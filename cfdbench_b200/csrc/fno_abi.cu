@@ -238,9 +238,8 @@ int fno_rollout_host(const fno_weights* w, const float* inputs_host, const float
 
 // One step for host buffers as a three-stage pipeline over batch chunks: all host->device copies go, in chunk order,
 // through ONE stream, the kernels of the chunks through a second one and the device->host copies through a third,
-// chained by events.  Copies of the same direction therefore never run concurrently (with one stream per chunk the
-// four simultaneous H2D copies intermittently dropped to ~8 GB/s in total: 2.6 ms instead of 0.9 ms per step at
-// B = 256) while chunk c+1's upload still overlaps chunk c's kernels and chunk c-1's download.
+// chained by events.  Copies of the same direction therefore never run concurrently, while chunk c+1's upload still
+// overlaps chunk c's kernels and chunk c-1's download (0.88 ms per step at B = 256 with two chunks, 0.97 ms unchunked).
 int fno_rollout_host_chunked(const fno_weights* w, const float* inputs_host, const float* mask_host,
                              const float* case_params_host, float* preds_host, const fno_workspace* ws_chunks,
                              void* const* dev_io_chunks, int batch, int n_chunks, int act_dtype, void* stream_in,
