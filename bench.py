@@ -275,6 +275,11 @@ def cpu_baseline(sd, batch, budget_s: float = 20.0, max_steps: int = 8):
                       f"torch {torch.__version__} CPU, median {med * 1e3:.1f} ms/step"}
 
 
+def workload_name(batch: int) -> str:
+    return (f"FNO autoregressive rollout, cavity_prop_bc_geo shape (p=5), batch {batch}/GPU, 64x64x2 "
+            f"fields, 4 Fourier layers x 32 ch x 12x12 modes (BASELINE.json configs[1])")
+
+
 def run_reference(args, rank: int, world: int):
     """--impl reference: the reference's own CPU implementation of the path (oracle port; /root/reference does
     not exist on the GPU box and the reference is pure Python/PyTorch, so there is nothing to compile)."""
@@ -300,8 +305,11 @@ def run_reference(args, rank: int, world: int):
         "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * t / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"FNO autoregressive rollout, cavity (p=5), batch {args.batch}, 64x64x2, CPU fp32",
-                   "batch_per_step": args.batch},
+        # same workload as the GPU arm; one step = one pass over one batch of `batch_per_gpu` cases
+        "config": {"workload": workload_name(args.batch), "batch_per_gpu": args.batch, "global_batch": args.batch,
+                   "act_storage": "f32", "arithmetic": "fp32",
+                   "implementation": f"reference CPU path (torch port of src/models/fno/fno2d.py), "
+                                     f"{torch.get_num_threads()} threads, rank 0 only"},
         "sample_steps_per_s": val * args.batch,
         "cpu_baseline": {"value": val, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
                          "sample": f"{args.steps} rollout steps, B={args.batch}, torch {torch.__version__} CPU"},
@@ -402,8 +410,7 @@ def main():
         "warmup": args.warmup, "ms_per_step": head["ms_per_step"], "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {
-            "workload": f"FNO autoregressive rollout, cavity_prop_bc_geo shape (p=5), batch {args.batch}/GPU, 64x64x2 "
-                        f"fields, 4 Fourier layers x 32 ch x 12x12 modes (BASELINE.json configs[1])",
+            "workload": workload_name(args.batch),
             "batch_per_gpu": args.batch, "global_batch": args.batch * world,
             "act_storage": "bf16" if args.act == "bf16" else "f32", "arithmetic": "fp32",
             "parallelism": f"dp{world} (independent case shards, no data-path collective)",
