@@ -37,11 +37,21 @@ sys.path.insert(0, ROOT)
 
 from cfdbench_b200 import dp, synth  # noqa: E402
 
-# dram__bytes_read.sum + dram__bytes_write.sum of one block_tc_kernel launch at B=256 from the `ncu --set full`
-# capture summarised in profiles/ncu_r01j.md (bf16 storage: 117.6 MB read + 35.8 MB written; the read side
-# includes the fp32 Z rows produced by inv_kx_kernel that are not part of the algorithmic byte count, and part of
-# the output is still in L2 when the kernel ends).
-NCU_TRAFFIC_BYTES = {("bf16", 256): 153320960}
+# roofline.traffic = dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the dominant kernel, read at run
+# time from the committed summary of the `ncu --set full` capture (profiles/ncu_traffic.json, written by
+# tools/summarize_profiles.py from the .ncu-rep).  Keyed by kernel name, activation storage and batch: if the kernel was
+# renamed / the workload changed since the capture, the lookup fails and traffic is reported as null with the reason.
+def ncu_traffic(kernel: str, act: str, batch: int):
+    path = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    try:
+        with open(path) as f:
+            table = json.load(f)
+    except Exception as e:  # noqa: BLE001
+        return None, f"profiles/ncu_traffic.json unreadable ({type(e).__name__})"
+    ent = table.get(f"{kernel}|{act}|{batch}")
+    if ent is None:
+        return None, f"no ncu capture of {kernel} at act={act}, B={batch} in profiles/ncu_traffic.json"
+    return int(ent["dram_bytes"]), ent.get("source", "")
 
 METRIC = "fno_rollout_steps_per_sec"
 UNIT = "steps/s"
@@ -116,7 +126,7 @@ def build_model(act: str, p: int, seed: int = 0):
     return m, sd
 
 
-def timed_rollout(model, inp, cp, mk, steps: int, warmup: int):
+def timed_rollout(model, inp, cp, mk, steps: int, warmup: int, reps: int = 5):
     """K steps = one native rollout of K steps on torch's current stream, CUDA events around it."""
     dev = model.device
     t_spin = time.perf_counter()  # bring the SM clocks up from idle before the contract's W warm-up steps
@@ -131,15 +141,18 @@ def timed_rollout(model, inp, cp, mk, steps: int, warmup: int):
     if torch.distributed.is_initialized():
         torch.distributed.barrier()
     torch.cuda.synchronize(dev)
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    seq = model.generate_many(inp, cp, mk, steps)
-    e1.record()
-    torch.cuda.synchronize(dev)
-    if torch.distributed.is_initialized():
-        torch.distributed.barrier()
-    torch.cuda.synchronize(dev)
-    return e0.elapsed_time(e1) / 1e3, seq
+    times = []
+    for _ in range(reps):   # every repetition times exactly K steps, barrier + synchronize on both sides
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        seq = model.generate_many(inp, cp, mk, steps)
+        e1.record()
+        torch.cuda.synchronize(dev)
+        if torch.distributed.is_initialized():
+            torch.distributed.barrier()
+        torch.cuda.synchronize(dev)
+        times.append(e0.elapsed_time(e1) / 1e3)
+    return times, seq
 
 
 def timed_e2e(model, batch: dict, steps: int, warmup: int):
@@ -162,7 +175,8 @@ def timed_e2e(model, batch: dict, steps: int, warmup: int):
 
 
 def kernel_pass(model, inp, cp, mk, steps: int):
-    """Second pass with CUDA events around every kernel launch (same stream): mean duration per kernel."""
+    """Second pass with CUDA events around every kernel launch (same stream, same C-ABI calls as fno_forward issues
+    for this model): mean duration per kernel."""
     from cfdbench_b200 import _lib
     lib = _lib.load()
     b = inp.shape[0]
@@ -173,7 +187,8 @@ def kernel_pass(model, inp, cp, mk, steps: int):
     st = model._stream()
     acts = [bufs["act0"], bufs["act1"]]
     preds = torch.empty(b, 2, 64, 64, device=model.device)
-    names = ["lift", "dft_fwd", "mode_mix", "inv_kx", "block_out", "project"]
+    fused = "ym_img" in bufs
+    names = ["lift", "dft_fwd", "mode_mix"] + (["block_fused"] if fused else ["inv_kx", "block_out"]) + ["project"]
     evs = {n: [] for n in names}
 
     def timed(name, fn):
@@ -191,11 +206,16 @@ def kernel_pass(model, inp, cp, mk, steps: int):
         cur = 0
         for l in range(model.num_layers):
             timed("dft_fwd", lambda: lib.fno_spectral_dft_fwd(acts[cur].data_ptr(), bufs["xm"].data_ptr(), b, act, 1.0, 1.0, st))
-            timed("mode_mix", lambda: lib.fno_mode_mix(bufs["xm"].data_ptr(), w.spec_wk[l], bufs["ym"].data_ptr(), b, st))
-            timed("inv_kx", lambda: lib.fno_spectral_inv_kx(bufs["ym"].data_ptr(), bufs["z"].data_ptr(), b, inv, 2 * inv, st))
-            timed("block_out", lambda: lib.fno_block_out(_lib.EPI_GELU, bufs["z"].data_ptr(), acts[cur].data_ptr(),
-                                                         w.w0t[l], w.w0_b[l], acts[cur ^ 1].data_ptr(), None, None, b,
-                                                         act, st))
+            if fused:
+                timed("mode_mix", lambda: lib.fno_mode_mix_image(bufs["xm"].data_ptr(), w.spec_wk[l], bufs["ym_img"].data_ptr(), b, st))
+                timed("block_fused", lambda: lib.fno_block_fused(bufs["ym_img"].data_ptr(), acts[cur].data_ptr(), w.w0t[l],
+                                                                 w.w0_b[l], acts[cur ^ 1].data_ptr(), b, st))
+            else:
+                timed("mode_mix", lambda: lib.fno_mode_mix(bufs["xm"].data_ptr(), w.spec_wk[l], bufs["ym"].data_ptr(), b, st))
+                timed("inv_kx", lambda: lib.fno_spectral_inv_kx(bufs["ym"].data_ptr(), bufs["z"].data_ptr(), b, inv, 2 * inv, st))
+                timed("block_out", lambda: lib.fno_block_out(_lib.EPI_GELU, bufs["z"].data_ptr(), acts[cur].data_ptr(),
+                                                             w.w0t[l], w.w0_b[l], acts[cur ^ 1].data_ptr(), None, None, b,
+                                                             act, st))
             cur ^= 1
         timed("project", lambda: lib.fno_project_fwd(acts[cur].data_ptr(), mk.data_ptr(), C.byref(w), preds.data_ptr(), b, act, st))
         cur_in = preds
@@ -257,22 +277,132 @@ def timed_train_step(p: int, batch_size: int, steps: int = 5, warmup: int = 3, f
                                                                    "torch.optim.Adam") + ".step, fp32 storage"}
 
 
-def cpu_baseline(sd, batch, budget_s: float = 20.0, max_steps: int = 8):
-    """The reference's CPU path (oracle port: same torch.fft / einsum / conv2d / gelu calls) on this host."""
+def host_cpu():
+    """(model string, physical cores, logical cpus) of this host."""
+    model = "unknown"
+    try:
+        with open("/proc/cpuinfo") as f:
+            for ln in f:
+                if ln.lower().startswith("model name"):
+                    model = ln.split(":", 1)[1].strip()
+                    break
+    except OSError:
+        pass
+    try:
+        import psutil
+        phys = psutil.cpu_count(logical=False) or os.cpu_count()
+    except Exception:  # noqa: BLE001
+        phys = os.cpu_count()
+    return model, int(phys or 1), int(os.cpu_count() or 1)
+
+
+def reference_impl(sd):
+    """The CPU implementation `cpu_baseline` / `--impl reference` time, as (kind, forward, train_step_factory).
+    kind "reference": the UNMODIFIED reference module, installed by __graft_entry__.build() from /root/reference/src into
+    the git-ignored baseline/_ref/ (it travels to the GPU box with the snapshot); kind "port": oracle/fno_torch_port.py,
+    verified bit-identical to it by oracle/make_golden.py, when baseline/_ref is absent."""
+    ref_src = os.path.join(ROOT, "baseline", "_ref", "src")
+    if os.path.isdir(os.path.join(ref_src, "models", "fno")):
+        try:
+            sys.path.insert(0, ref_src)
+            rs = torch.random.get_rng_state()
+            from models.fno.fno2d import Fno2d as RefFno2d   # seeds the global RNGs at import (fno2d.py:13-14)
+            from models.loss import loss_name_to_fn as ref_loss
+            torch.random.set_rng_state(rs)
+            p = sd["fc0.weight"].shape[1] - 5
+            m = RefFno2d(in_chan=2, out_chan=2, n_case_params=p, loss_fn=ref_loss("nmse"), num_layers=synth.DEPTH,
+                         hidden_dim=synth.HIDDEN, modes1=synth.MODES, modes2=synth.MODES)
+            m.load_state_dict({k: torch.from_numpy(v) for k, v in sd.items()})
+            m.eval()
+
+            def fwd(inp, cp, mk):
+                return m.generate(inputs=inp, case_params=cp, mask=mk)
+
+            def many(inp, cp, mk, steps):
+                return m.generate_many(inp, cp, mk, steps)
+
+            def make_train():
+                opt_ = torch.optim.Adam(m.parameters(), lr=1e-4)
+
+                def step(tb):
+                    out = m(**tb)
+                    out["loss"]["nmse"].backward()
+                    opt_.step()
+                    opt_.zero_grad()
+                    return out["loss"]["nmse"].item()
+                return step
+            return "reference", fwd, many, make_train
+        except Exception as e:  # noqa: BLE001
+            sys.stderr.write(f"bench.py: baseline/_ref unusable ({type(e).__name__}: {e}); timing the oracle port\n")
+        finally:
+            if sys.path and sys.path[0] == ref_src:
+                sys.path.pop(0)
     from oracle import fno_torch_port as opt
     pp = opt.params_from_numpy(sd)
+
+    def fwd(inp, cp, mk):
+        return opt.forward(pp, inp, cp, mk)["preds"]
+
+    def many(inp, cp, mk, steps):
+        return opt.rollout(pp, inp, cp, mk, steps)
+
+    def make_train():
+        pg = opt.params_from_numpy(sd, requires_grad=True)
+        opt_ = torch.optim.Adam(list(pg.values()), lr=1e-4)
+        return lambda tb: opt.train_step(pg, opt_, tb)
+    return "port", fwd, many, make_train
+
+
+def _median_time(fn, n_warm, n_iter, budget_s):
+    for _ in range(n_warm):
+        fn()
+    ts, t_start = [], time.perf_counter()
+    while len(ts) < n_iter and (time.perf_counter() - t_start) < budget_s:
+        t0 = time.perf_counter()
+        fn()
+        ts.append(time.perf_counter() - t0)
+    return float(np.median(ts)), len(ts)
+
+
+def cpu_baseline(sd, batch, budget_s: float = 12.0, max_steps: int = 6):
+    """The reference's CPU path on this host's cores (SURVEY.md 8d / BASELINE.md section 3): the headline workload
+    (B=256 rollout step) on a bounded sample, plus config (1) B=1 single step, the B=1 20-step generate_many of
+    test_multistep.py:144-149, the B=8 train step of train_auto.py:233-260, and the 1-thread figure."""
+    kind, fwd, many, make_train = reference_impl(sd)
+    cpu_model, phys, logical = host_cpu()
+    prev_threads = torch.get_num_threads()
+    torch.set_num_threads(phys)
     inp, cp, mk = (torch.from_numpy(batch[k]) for k in ("inputs", "case_params", "mask"))
+    out = {}
     with torch.no_grad():
-        opt.forward(pp, inp, cp, mk)  # warm-up
-        ts, cur, t_start = [], inp, time.perf_counter()
-        while len(ts) < max_steps and (time.perf_counter() - t_start) < budget_s:
-            t0 = time.perf_counter()
-            cur = opt.forward(pp, cur, cp, mk)["preds"]
-            ts.append(time.perf_counter() - t0)
-    med = float(np.median(ts))
-    return {"value": 1.0 / med, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
-            "sample": f"{len(ts)} rollout steps of the same B={inp.shape[0]} cavity batch, fp32, "
-                      f"torch {torch.__version__} CPU, median {med * 1e3:.1f} ms/step"}
+        cur = [inp]
+
+        def step256():
+            cur[0] = fwd(cur[0], cp, mk)
+        med, n = _median_time(step256, 1, max_steps, budget_s)
+        out.update({"value": 1.0 / med, "unit": UNIT, "cores": phys, "kind": kind, "cpu_model": cpu_model,
+                    "logical_cpus": logical,
+                    "sample": f"{n} rollout steps of the same B={inp.shape[0]} cavity batch, fp32, torch {torch.__version__} "
+                              f"CPU, {phys} threads, median {med * 1e3:.1f} ms/step"})
+        i1, c1, m1 = inp[:1], cp[:1], mk[:1]
+        med1, n1 = _median_time(lambda: fwd(i1, c1, m1), 5, 30, 3.0)
+        med20, n20 = _median_time(lambda: many(i1[0], c1[0], m1[0, 0] if m1.dim() == 4 else m1[0], 20), 1, 5, 4.0)
+        torch.set_num_threads(1)
+        med1t, n1t = _median_time(lambda: fwd(i1, c1, m1), 3, 20, 3.0)
+        torch.set_num_threads(phys)
+    b8 = synth.make_batch(11, 8, "cavity")
+    tb8 = {k: torch.from_numpy(v) for k, v in b8.items()}
+    train = make_train()
+    medt, nt = _median_time(lambda: train(tb8), 2, 10, 4.0)
+    out["others"] = {
+        "b1_generate_ms": {"median": med1 * 1e3, "iters": n1, "threads": phys},                    # BASELINE config (1)
+        "b1_generate_1thread_ms": {"median": med1t * 1e3, "iters": n1t, "threads": 1},
+        "b1_generate_many_20_steps_ms": {"median": med20 * 1e3, "iters": n20, "threads": phys},
+        "b8_train_step_ms": {"median": medt * 1e3, "iters": nt, "threads": phys,
+                             "what": "fwd + nmse.backward + Adam.step + zero_grad + .item()"},
+    }
+    torch.set_num_threads(prev_threads)
+    return out
 
 
 def workload_name(batch: int) -> str:
@@ -281,26 +411,28 @@ def workload_name(batch: int) -> str:
 
 
 def run_reference(args, rank: int, world: int):
-    """--impl reference: the reference's own CPU implementation of the path (oracle port; /root/reference does
-    not exist on the GPU box and the reference is pure Python/PyTorch, so there is nothing to compile)."""
+    """--impl reference: the reference's own CPU implementation of the path (the unmodified module from baseline/_ref when
+    build() could install it, else the verified port) on ALL physical cores of this host -- also under torchrun, where
+    OMP_NUM_THREADS=1 would otherwise leave it single-threaded.  Rank 0 only; the other ranks exit."""
     if rank != 0:
         return
-    # torch's default thread count = physical cores; using all SMT threads is 3x slower for this workload
-    from oracle import fno_torch_port as opt
+    cpu_model, phys, logical = host_cpu()
+    torch.set_num_threads(phys)
     p = synth.n_case_params("cavity")
     sd = synth.make_state_dict(0, n_params=p)
     batch = synth.make_batch(1, args.batch, "cavity", with_label=False)
-    pp = opt.params_from_numpy(sd)
+    kind, fwd, _, _ = reference_impl(sd)
     inp, cp, mk = (torch.from_numpy(batch[k]) for k in ("inputs", "case_params", "mask"))
     cur = inp
     with torch.no_grad():
         for _ in range(args.warmup):
-            cur = opt.forward(pp, cur, cp, mk)["preds"]
+            cur = fwd(cur, cp, mk)
         t0 = time.perf_counter()
         for _ in range(args.steps):
-            cur = opt.forward(pp, cur, cp, mk)["preds"]
+            cur = fwd(cur, cp, mk)
         t = time.perf_counter() - t0
     val = args.steps / t
+    threads = torch.get_num_threads()
     line = {
         "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * t / args.steps, "higher_is_better": True, "scaling": "weak",
@@ -308,10 +440,10 @@ def run_reference(args, rank: int, world: int):
         # same workload as the GPU arm; one step = one pass over one batch of `batch_per_gpu` cases
         "config": {"workload": workload_name(args.batch), "batch_per_gpu": args.batch, "global_batch": args.batch,
                    "act_storage": "f32", "arithmetic": "fp32",
-                   "implementation": f"reference CPU path (torch port of src/models/fno/fno2d.py), "
-                                     f"{torch.get_num_threads()} threads, rank 0 only"},
+                   "implementation": (f"reference CPU path ({'unmodified src/models/fno/fno2d.py from baseline/_ref' if kind == 'reference' else 'torch port of src/models/fno/fno2d.py'}), "
+                                      f"{threads} threads on {cpu_model} ({phys} cores), rank 0 only")},
         "sample_steps_per_s": val * args.batch,
-        "cpu_baseline": {"value": val, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "kind": kind, "cpu_model": cpu_model,
                          "sample": f"{args.steps} rollout steps, B={args.batch}, torch {torch.__version__} CPU"},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -356,11 +488,11 @@ def main():
         headline = act == args.act
         if headline and rank == 0:
             sampler.start()
-        t, _ = timed_rollout(model, inp, cp, mk, args.steps, args.warmup)
+        ts, _ = timed_rollout(model, inp, cp, mk, args.steps, args.warmup, reps=5 if headline else 3)
         if headline and rank == 0:
             clocks = sampler.stop()
-        t_max = dp.max_over_ranks(t, dev)
-        r = {"t": t_max}
+        ts_max = [dp.max_over_ranks(t, dev) for t in ts]   # max over ranks of every repetition
+        r = {"t": float(np.median(ts_max)), "t_min": float(min(ts_max)), "t_all": ts_max}
         if headline:
             # Before any CPU-side oracle work: the intra-op worker threads of a torch CPU op keep spinning for ~200 ms
             # after it returns, and a host loop of ~40 driver calls per step started in that window ran 3-4x slower
@@ -386,19 +518,32 @@ def main():
 
     def summarize(act):
         r = results[act]
+        k = r["kernels"]
         elt = 2 if act == "bf16" else 4
-        k3 = r["kernels"]["block_out"]["mean_us"] * 1e-6
+        fused = "block_fused" in k
+        dom = "block_fused" if fused else "block_out"
+        dom_kernel = "block_fused_kernel" if fused else "block_tc_kernel"
+        k3 = k[dom]["mean_us"] * 1e-6
         alg = args.batch * 32 * HW * 2 * elt  # 32*64*64*(s_in+s_out) per sample-layer x samples/launch
-        blk = sum(r["kernels"][n]["mean_us"] for n in ("dft_fwd", "mode_mix", "inv_kx", "block_out")) * 1e-6
-        step_us = sum(v["mean_us"] * v["launches_per_step"] for v in r["kernels"].values())
+        layer = [n for n in ("dft_fwd", "mode_mix", "inv_kx", "block_out", "block_fused") if n in k]
+        blk = sum(k[n]["mean_us"] for n in layer) * 1e-6
+        step_us = sum(v["mean_us"] * v["launches_per_step"] for v in k.values())
+        # SURVEY 8d whole-step algorithmic bytes per sample (layer-fused design): 2,662,400 B with bf16 storage
+        step_alg = args.batch * (3 * HW * 2 + 32 * HW * elt + 4 * 32 * HW * 2 * elt + 32 * HW * elt + 2 * HW * 4) if act == "f32" \
+            else args.batch * 2662400
+        ms = 1e3 * r["t"] / args.steps
+        traffic, traffic_src = ncu_traffic(dom_kernel, act, args.batch)
         return {
-            "value": world * args.steps / r["t"], "ms_per_step": 1e3 * r["t"] / args.steps,
-            "roofline": {"bound": "hbm", "kernel": "block_tc_kernel", "achieved": alg / k3 / 1e9, "peak": peak,
-                         "unit": "GB/s", "frac": alg / k3 / 1e9 / peak, "traffic": NCU_TRAFFIC_BYTES.get((act, args.batch)),
+            "value": world * args.steps / r["t"], "ms_per_step": ms, "ms_per_step_min": 1e3 * r["t_min"] / args.steps,
+            "reps_ms_per_step": [1e3 * t / args.steps for t in r["t_all"]],
+            "roofline": {"bound": "hbm", "kernel": dom_kernel, "achieved": alg / k3 / 1e9, "peak": peak,
+                         "unit": "GB/s", "frac": alg / k3 / 1e9 / peak, "traffic": traffic, "traffic_source": traffic_src,
                          "algorithmic_bytes_per_launch": alg, "peak_source": peak_src,
-                         "share_of_step": r["kernels"]["block_out"]["mean_us"] * 4 / step_us,
-                         "fourier_layer_frac": alg / blk / 1e9 / peak},
-            "kernels": r["kernels"], "rel_l2": r["rel_l2"],
+                         "share_of_step": k[dom]["mean_us"] * k[dom]["launches_per_step"] / step_us,
+                         "fourier_layer_frac": alg / blk / 1e9 / peak, "fourier_layer_us": blk * 1e6,
+                         "step_frac": step_alg / (ms * 1e-3) / 1e9 / peak, "step_algorithmic_bytes": step_alg},
+            "kernels": k, "rel_l2": r["rel_l2"],
+            "launches_per_step": sum(v["launches_per_step"] for v in k.values()),
         }
 
     head = summarize(args.act)
@@ -408,19 +553,23 @@ def main():
     line = {
         "metric": METRIC, "value": head["value"], "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": head["ms_per_step"], "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "vs_baseline": None, "dtype": "bf16" if args.act == "bf16" else "f32", "data": "synthetic",
         "config": {
             "workload": workload_name(args.batch),
             "batch_per_gpu": args.batch, "global_batch": args.batch * world,
-            "act_storage": "bf16" if args.act == "bf16" else "f32", "arithmetic": "fp32",
+            "act_storage": "bf16" if args.act == "bf16" else "f32",
+            "arithmetic": "fp32-grade: tensor-core products as 3xTF32 / bf16x3 (24-bit operands), fp32 accumulation",
             "parallelism": f"dp{world} (independent case shards, no data-path collective)",
             "l2": "inputs larger than L2: per-step working set (2 activation buffers + modes) = "
                   f"{(2 * args.batch * 32 * HW * (2 if args.act == 'bf16' else 4) + 2 * args.batch * 288 * 32 * 8) / 1e6:.0f} MB > 126 MB",
             "cuda_graph": not args.no_graph,
+            "timing": "median of 5 repetitions of K steps each (CUDA events, max over ranks per repetition); "
+                      "ms_per_step_min / reps_ms_per_step alongside",
         },
         "sample_steps_per_s": head["value"] * args.batch,
+        "ms_per_step_min": head["ms_per_step_min"], "reps_ms_per_step": head["reps_ms_per_step"],
         "e2e": {"value": world * args.steps / te, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
-        "gpu_launches": args.steps * (2 + 4 * synth.DEPTH),
+        "gpu_launches": args.steps * head["launches_per_step"],
         "roofline": head["roofline"], "kernels": head["kernels"], "rel_l2": head["rel_l2"],
         ("fp32_storage" if other_act == "f32" else "bf16_storage"): other,
         "train_step": train,

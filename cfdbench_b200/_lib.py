@@ -11,6 +11,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libcfdbench_b200.so")
 
 FNO_MAX_LAYERS = 8
+ABI_VERSION = 2
 ACT_F32, ACT_BF16 = 0, 1
 EPI_GELU, EPI_GELU_SAVE_PRE, EPI_MUL_DGELU, EPI_PLAIN = 0, 1, 2, 3
 
@@ -34,7 +35,8 @@ class FnoWeights(C.Structure):
 
 
 class FnoWorkspace(C.Structure):
-    _fields_ = [("act", C.c_void_p * 2), ("xm", C.c_void_p), ("ym", C.c_void_p), ("z", C.c_void_p)]
+    _fields_ = [("act", C.c_void_p * 2), ("xm", C.c_void_p), ("ym", C.c_void_p), ("z", C.c_void_p),
+                ("ym_img", C.c_void_p)]
 
 
 class FnoGrads(C.Structure):
@@ -88,6 +90,9 @@ SIGNATURES = {
     "fno_act_bytes": (C.c_size_t, [_I, _I]),
     "fno_modes_bytes": (C.c_size_t, [_I]),
     "fno_z_bytes": (C.c_size_t, [_I]),
+    "fno_ym_image_bytes": (C.c_size_t, [_I]),
+    "fno_mode_mix_image": (C.c_int, [_P, _P, _P, _I, _P]),
+    "fno_block_fused": (C.c_int, [_P, _P, _P, _P, _P, _I, _P]),
     "fno_pack_spectral_weights": (C.c_int, [_P, _P, _P, _I, _P]),
     "fno_unpack_spectral_grads": (C.c_int, [_P, _P, _P, _P]),
     "fno_mix_operand_bytes": (C.c_size_t, []),
@@ -142,8 +147,8 @@ def load() -> C.CDLL:
         fn = getattr(lib, name)  # AttributeError if the .so does not export a declared symbol
         fn.restype = res
         fn.argtypes = args
-    if lib.fno_version() != 1:
-        raise FnoNativeError(f"ABI version mismatch: library reports {lib.fno_version()}, wrapper expects 1")
+    if lib.fno_version() != ABI_VERSION:
+        raise FnoNativeError(f"ABI version mismatch: library reports {lib.fno_version()}, wrapper expects {ABI_VERSION}")
     _lib = lib
     return lib
 

@@ -8,7 +8,9 @@
 namespace fno {
 template <typename TAct>
 cudaError_t launch_dft_fwd(const void*, void*, int, float, float, cudaStream_t);
-cudaError_t launch_mode_mix(const void*, const void*, void*, int, cudaStream_t);
+cudaError_t launch_mode_mix(const void*, const void*, void*, void*, int, cudaStream_t);
+cudaError_t launch_block_fused(const void*, const void*, const float*, const float*, void*, int, cudaStream_t);
+size_t ym_image_bytes(int);
 cudaError_t launch_pack_spectral(const void*, const void*, void*, int, cudaStream_t);
 cudaError_t launch_unpack_spectral(const void*, void*, void*, cudaStream_t);
 cudaError_t launch_dft_fwd_tc(const void*, void*, int, float, float, cudaStream_t);
@@ -77,6 +79,7 @@ size_t fno_act_bytes(int batch, int act_dtype) {
 }
 size_t fno_modes_bytes(int batch) { return static_cast<size_t>(batch) * kModes * kC * sizeof(float2); }
 size_t fno_z_bytes(int batch) { return static_cast<size_t>(batch) * kH * 2 * kM2 * kC * sizeof(float); }
+size_t fno_ym_image_bytes(int batch) { return ym_image_bytes(batch); }
 
 int fno_pack_spectral_weights(const void* w1, const void* w2, void* wk, int conj_transpose, void* stream) {
   if (!w1 || !w2 || !wk) return fail(kErrArg, "fno_pack_spectral_weights: null pointer");
@@ -134,7 +137,20 @@ int fno_spectral_dft_fwd_tc(const void* act_in_bf16, void* xm, int batch, float 
 
 int fno_mode_mix(const void* xm, const void* wk, void* ym, int batch, void* stream) {
   if (!xm || !wk || !ym || batch <= 0) return fail(kErrArg, "fno_mode_mix: bad argument");
-  FNO_CUDA(launch_mode_mix(xm, wk, ym, batch, S(stream)), "mode_mix_tc_kernel");
+  FNO_CUDA(launch_mode_mix(xm, wk, ym, nullptr, batch, S(stream)), "mode_mix_tc_kernel");
+  return kOk;
+}
+
+int fno_mode_mix_image(const void* xm, const void* wk, void* ym_img, int batch, void* stream) {
+  if (!xm || !wk || !ym_img || batch <= 0) return fail(kErrArg, "fno_mode_mix_image: bad argument");
+  FNO_CUDA(launch_mode_mix(xm, wk, nullptr, ym_img, batch, S(stream)), "mode_mix_tc_kernel(image)");
+  return kOk;
+}
+
+int fno_block_fused(const void* ym_img, const void* act_in, const float* w0t, const float* bias, void* act_out, int batch,
+                    void* stream) {
+  if (!ym_img || !act_in || !w0t || !act_out || batch <= 0) return fail(kErrArg, "fno_block_fused: bad argument");
+  FNO_CUDA(launch_block_fused(ym_img, act_in, w0t, bias, act_out, batch, S(stream)), "block_fused_kernel");
   return kOk;
 }
 
@@ -162,6 +178,10 @@ int fno_block_fwd(const fno_weights* w, int layer, const void* act_in, void* act
                   const fno_workspace* ws, int batch, int act_dtype, void* stream) {
   if (!w || !ws || layer < 0 || layer >= w->n_layers) return fail(kErrArg, "fno_block_fwd: bad argument");
   FNO_TRY(fno_spectral_dft_fwd(act_in, ws->xm, batch, act_dtype, 1.f, 1.f, stream));
+  if (act_dtype == FNO_ACT_BF16 && ws->ym_img && !pre_out) {   // inference, bf16 storage: fused output stage
+    FNO_TRY(fno_mode_mix_image(ws->xm, w->spec_wk[layer], ws->ym_img, batch, stream));
+    return fno_block_fused(ws->ym_img, act_in, w->w0t[layer], w->w0_b[layer], act_out, batch, stream);
+  }
   FNO_TRY(fno_mode_mix(ws->xm, w->spec_wk[layer], ws->ym, batch, stream));
   const float inv = 1.f / static_cast<float>(kHW);
   FNO_TRY(fno_spectral_inv_kx(ws->ym, ws->z, batch, inv, 2.f * inv, stream));
@@ -183,7 +203,8 @@ int fno_project_fwd(const void* act_in, const float* mask, const fno_weights* w,
 
 int fno_forward(const fno_weights* w, const float* inputs, const float* mask, const float* case_params,
                 float* preds, const fno_workspace* ws, int batch, int act_dtype, void* stream) {
-  if (!w || !ws || !ws->act[0] || !ws->act[1] || !ws->xm || !ws->ym || !ws->z) return fail(kErrArg, "fno_forward: bad workspace");
+  if (!w || !ws || !ws->act[0] || !ws->act[1] || !ws->xm) return fail(kErrArg, "fno_forward: bad workspace");
+  if (!(act_dtype == FNO_ACT_BF16 && ws->ym_img) && (!ws->ym || !ws->z)) return fail(kErrArg, "fno_forward: bad workspace");
   if (w->n_layers < 1 || w->n_layers > FNO_MAX_LAYERS) return fail(kErrUnsupported, "fno_forward: n_layers out of range");
   FNO_TRY(fno_lift_fwd(inputs, mask, case_params, w, ws->act[0], batch, act_dtype, stream));
   int cur = 0;

@@ -89,7 +89,8 @@ __device__ __forceinline__ void mx_group_barrier() {
 
 template <int GRP>
 __device__ __forceinline__ void mx_pipeline(MxSmem& sm, const float4* __restrict__ xm, const float* __restrict__ wop,
-                                            float4* __restrict__ ym, int batch, int n_btiles, int n_tiles) {
+                                            float4* __restrict__ ym, unsigned char* __restrict__ ym_img, int batch,
+                                            int n_btiles, int n_tiles) {
   const int tid = threadIdx.x, lane = tid & 31;
   const int gtid = tid & (kMxGroup - 1), gwarp = tc::warp_index_uniform() & 7;
   const uint32_t tmem_base = sm.tmem_base + GRP * (2 * kMxN);
@@ -112,10 +113,31 @@ __device__ __forceinline__ void mx_pipeline(MxSmem& sm, const float4* __restrict
     float v[32];
     tc::tmem_ld32(tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + buf * kMxN + half * 32, v);
     tc::fence_before_thread_sync();
-    if (b < batch) {
+    if (b < batch && ym_img == nullptr) {
       float4* dst = ym + (static_cast<size_t>(k) * batch + b) * (kC / 2) + half * 8;
 #pragma unroll
       for (int c = 0; c < 8; ++c) dst[c] = make_float4(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
+    } else if (b < batch) {
+      // Operand image of block_fused_kernel's GEMM1 (fno_block_fused.cu): per sample [hi|lo][ky/4][ky%4][48 rows][32 o]
+      // fp32, row = 24 (kxi & 1) + 2 (kxi >> 1) + (re|im), 32-byte chunks XOR-swizzled with (row & 3); tf32 hi / lo
+      // split here so the consumer is pure bulk copy + MMA.  This thread holds o = 16 half .. 16 half + 15, (re, im).
+      const int kxi = k / kM2, ky = k % kM2;
+      unsigned char* img = ym_img + static_cast<size_t>(b) * 147456 + (ky >> 2) * 24576 + (ky & 3) * 6144;
+#pragma unroll
+      for (int ri = 0; ri < 2; ++ri) {
+        const int row = 24 * (kxi & 1) + 2 * (kxi >> 1) + ri;
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+          float hi[8], lo[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) tc::split_tf32(v[2 * (8 * c + j) + ri], hi[j], lo[j]);
+          unsigned char* dst = img + row * 128 + (((2 * half + c) ^ (row & 3)) << 5);
+          reinterpret_cast<float4*>(dst)[0] = make_float4(hi[0], hi[1], hi[2], hi[3]);
+          reinterpret_cast<float4*>(dst)[1] = make_float4(hi[4], hi[5], hi[6], hi[7]);
+          reinterpret_cast<float4*>(dst + 73728)[0] = make_float4(lo[0], lo[1], lo[2], lo[3]);
+          reinterpret_cast<float4*>(dst + 73728)[1] = make_float4(lo[4], lo[5], lo[6], lo[7]);
+        }
+      }
     }
   };
 
@@ -180,8 +202,8 @@ __device__ __forceinline__ void mx_pipeline(MxSmem& sm, const float4* __restrict
 }
 
 __global__ void __launch_bounds__(kMxThreads, 1)
-    mode_mix_tc_kernel(const float4* __restrict__ xm, const float* __restrict__ wop, float4* __restrict__ ym, int batch,
-                       int n_btiles, int n_tiles) {
+    mode_mix_tc_kernel(const float4* __restrict__ xm, const float* __restrict__ wop, float4* __restrict__ ym,
+                       unsigned char* __restrict__ ym_img, int batch, int n_btiles, int n_tiles) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];  // no pointer arithmetic: keeps LDS/STS addressing
   MxSmem& sm = *reinterpret_cast<MxSmem*>(smem_raw);
   if ((smem_u32(smem_raw) & 127u) != 0) __trap();
@@ -211,14 +233,15 @@ __global__ void __launch_bounds__(kMxThreads, 1)
   }
   pdl_wait();  // xm comes from the previous kernel of the chain
   pdl_launch_dependents();
-  if (grp == 0) mx_pipeline<0>(sm, xm, wop, ym, batch, n_btiles, n_tiles);
-  else mx_pipeline<1>(sm, xm, wop, ym, batch, n_btiles, n_tiles);
+  if (grp == 0) mx_pipeline<0>(sm, xm, wop, ym, ym_img, batch, n_btiles, n_tiles);
+  else mx_pipeline<1>(sm, xm, wop, ym, ym_img, batch, n_btiles, n_tiles);
   tc::fence_before_thread_sync();
   __syncthreads();
   if (warp == 0) tc::tmem_dealloc<4 * kMxN>(sm.tmem_base);
 }
 
-cudaError_t launch_mode_mix(const void* xm, const void* wop, void* ym, int batch, cudaStream_t stream) {
+// ym_img != nullptr: write the per-sample GEMM1 operand image (see the epilogue) instead of the mode-major ym.
+cudaError_t launch_mode_mix(const void* xm, const void* wop, void* ym, void* ym_img, int batch, cudaStream_t stream) {
   auto kern = mode_mix_tc_kernel;
   constexpr size_t smem = sizeof(MxSmem);
   static bool configured = false;
@@ -236,7 +259,8 @@ cudaError_t launch_mode_mix(const void* xm, const void* wop, void* ym, int batch
   const int n_tiles = kModes * n_btiles;
   const int grid = n_tiles < 2 * n_sm ? (n_tiles + 1) / 2 : n_sm;
   return launch_chained(kern, dim3(grid), dim3(kMxThreads), smem, stream, static_cast<const float4*>(xm),
-                        static_cast<const float*>(wop), static_cast<float4*>(ym), batch, n_btiles, n_tiles);
+                        static_cast<const float*>(wop), static_cast<float4*>(ym), static_cast<unsigned char*>(ym_img), batch,
+                        n_btiles, n_tiles);
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -149,6 +149,7 @@ class Fno2d(AutoCfdModel):
         # step replayed as one graph (B=256: 591 -> 544 us/step, B=1: 2.09 -> 1.48 ms per 20 steps).  False = launch
         # every kernel on the stream.
         self.graph_rollout = True
+        self.fused_block = True  # bf16 storage, inference: inv_kx + block_tc replaced by block_fused_kernel
         self.max_graphs = 8
         self.host_chunks = 2  # batch chunks of the pipelined host-tensor rollout path (upload | kernels | download)
         self._graphs: dict = {}
@@ -230,7 +231,7 @@ class Fno2d(AutoCfdModel):
         return wop
 
     def _workspace(self, batch: int, slot: int = 0):
-        key = (batch, self.act_dtype, self.device, slot)
+        key = (batch, self.act_dtype, self.device, slot, self.fused_block)
         ws = self._ws_cache.get(key)
         if ws is None:
             dev = self.device
@@ -245,6 +246,10 @@ class Fno2d(AutoCfdModel):
             st = _lib.FnoWorkspace()
             st.act[0], st.act[1] = bufs["act0"].data_ptr(), bufs["act1"].data_ptr()
             st.xm, st.ym, st.z = bufs["xm"].data_ptr(), bufs["ym"].data_ptr(), bufs["z"].data_ptr()
+            if self.act_dtype == "bfloat16" and self.fused_block:
+                # operand image of the fused output stage (fno_block_fused): inference never touches ym / z then
+                bufs["ym_img"] = torch.empty(_lib.load().fno_ym_image_bytes(batch), dtype=torch.uint8, device=dev)
+                st.ym_img = bufs["ym_img"].data_ptr()
             ws = (st, bufs)
             if len(self._ws_cache) > 16:
                 self._ws_cache.clear()

@@ -34,7 +34,7 @@
 extern "C" {
 #endif
 
-#define FNO_ABI_VERSION 1
+#define FNO_ABI_VERSION 2
 #define FNO_MAX_LAYERS 8
 
 enum { FNO_ACT_F32 = 0, FNO_ACT_BF16 = 1 };
@@ -64,6 +64,8 @@ typedef struct fno_workspace {
   void* xm;     /* B*288*32 complex64 */
   void* ym;     /* B*288*32 complex64 */
   void* z;      /* B*64*24*32 float32: rows of the half-inverted spectrum, Z[b][h][2 ky + (re|im)][o] */
+  void* ym_img; /* fno_ym_image_bytes(B), or NULL.  When set and act_dtype == FNO_ACT_BF16, inference blocks take the
+                 * fused output stage (fno_mode_mix_image + fno_block_fused) and `ym` / `z` are not touched. */
 } fno_workspace;
 
 int fno_version(void);
@@ -72,6 +74,7 @@ const char* fno_last_error(void);
 size_t fno_act_bytes(int batch, int act_dtype);
 size_t fno_modes_bytes(int batch);
 size_t fno_z_bytes(int batch);
+size_t fno_ym_image_bytes(int batch);
 
 /* weights1, weights2: (32,32,12,12) complex64 as stored by the reference (fno2d.py:31-51).
  * conj_transpose=0 -> wk[k][i][o] = W[i][o][k] (forward); 1 -> wk[k][o][i] = conj(W[i][o][k]) (adjoint). */
@@ -106,6 +109,15 @@ int fno_spectral_inv_kx(const void* ym, void* z, int batch, float s0, float s1, 
  *     (fno2d.py:81,104-111) as one tensor-core GEMM per 128-pixel tile.  pre_out/pre_in: see FNO_EPI_*. */
 int fno_block_out(int epilogue, const void* z, const void* act_in, const float* w0t, const float* bias, void* act_out,
                   float* pre_out, const float* pre_in, int batch, int act_dtype, void* stream);
+/* bf16 storage, inference: the output stage of a Fourier block in ONE kernel (block_fused_kernel, fno_block_fused.cu)
+ * -- replaces fno_spectral_inv_kx + fno_block_out(FNO_EPI_GELU), i.e. irfft2 + Conv2d(32,32,1) + add + GELU of
+ * reference src/models/fno/fno2d.py:81,104-111, without the Z round trip through HBM.
+ *   fno_mode_mix_image: same product as fno_mode_mix, written as the per-sample tensor-core operand image the fused
+ *     kernel bulk-copies (tf32 hi/lo split, fno_ym_image_bytes(B) bytes).
+ *   fno_block_fused:    act_out = GELU(irfft2(pad(Y)) + W0 act_in + bias); act_in / act_out bf16 [B][32][64][64]. */
+int fno_mode_mix_image(const void* xm, const void* wop, void* ym_img, int batch, void* stream);
+int fno_block_fused(const void* ym_img, const void* act_in_bf16, const float* w0t, const float* bias, void* act_out_bf16,
+                    int batch, void* stream);
 /* all four: act_out = FnoBlock_l(act_in) */
 int fno_block_fwd(const fno_weights* w, int layer, const void* act_in, void* act_out, float* pre_out,
                   const fno_workspace* ws, int batch, int act_dtype, void* stream);

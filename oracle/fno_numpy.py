@@ -119,16 +119,28 @@ def num_layers(sd: dict) -> int:
     return 1 + max(int(k.split(".")[1]) for k in sd if k.startswith("blocks."))
 
 
+def bf16_round(x: np.ndarray) -> np.ndarray:
+    """Round to the nearest bf16 value (ties to even), result as float64."""
+    u = np.ascontiguousarray(x, dtype=np.float32).view(np.uint32)
+    u = (u + np.uint32(0x7FFF) + ((u >> np.uint32(16)) & np.uint32(1))) & np.uint32(0xFFFF0000)
+    return u.view(np.float32).astype(np.float64)
+
+
 def fno_forward(sd: dict, inputs: np.ndarray, case_params: np.ndarray, mask: np.ndarray | None = None,
-                label: np.ndarray | None = None, normalize: bool = True, return_acts: bool = False):
-    """Fno2d.forward (reference fno2d.py:178-242).  Returns {"preds", ["loss"], ["acts"]}."""
+                label: np.ndarray | None = None, normalize: bool = True, return_acts: bool = False,
+                round_fn=None):
+    """Fno2d.forward (reference fno2d.py:178-242).  Returns {"preds", ["loss"], ["acts"]}.
+    `round_fn` (e.g. bf16_round) is applied to the hidden activations a_0..a_L, the tensors the CUDA path stores between
+    kernels: float64 arithmetic + bf16 storage = a second, torch-independent "bf16-boundary oracle"."""
     b, _, h, w = inputs.shape
     m = np.ones((b, 1, h, w)) if mask is None else (mask[:, None] if mask.ndim == 3 else mask)
     m = m.astype(np.float64)
-    a = conv1x1(lift_features(inputs, case_params, m), sd["fc0.weight"], sd["fc0.bias"])
+    rf = round_fn if round_fn is not None else (lambda t: t)
+    a = rf(conv1x1(lift_features(inputs, case_params, m), sd["fc0.weight"], sd["fc0.bias"]))
     acts, pres = [a], []
     for l in range(num_layers(sd)):
         a, pre = fno_block(a, sd, l, return_pre=True)
+        a = rf(a)
         acts.append(a)
         pres.append(pre)
     z1 = conv1x1(a, sd["fc1.weight"], sd["fc1.bias"])

@@ -114,3 +114,9 @@ def train_step(p: dict, opt: torch.optim.Optimizer, batch: dict) -> float:
 
 def bf16_round(t: torch.Tensor) -> torch.Tensor:
     return t.bfloat16().float()
+
+
+def bf16_round_ste(t: torch.Tensor) -> torch.Tensor:
+    """bf16 rounding with a straight-through gradient: what the CUDA training path does when activations are stored
+    as bf16 (the next layer consumes the rounded value, the backward pass differentiates the unrounded expression)."""
+    return t + (t.bfloat16().float() - t).detach()

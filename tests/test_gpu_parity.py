@@ -62,7 +62,8 @@ def rel(a, ref):
 def test_native_library_is_loaded(lib):
     from cfdbench_b200 import _lib
     assert os.path.exists(_lib.LIB_PATH)
-    assert lib.fno_version() == 1
+    from cfdbench_b200 import _lib as _l
+    assert lib.fno_version() == _l.ABI_VERSION
 
 
 @pytest.mark.parametrize("batch", [1, 3])
@@ -321,21 +322,7 @@ def test_host_rollout_and_graph_rollout_equal_device_rollout():
         assert torch.equal(a, b) and torch.equal(a, c)
 
 
-def test_bf16_storage_mode_against_bf16_boundary_oracle():
-    """bf16 hidden activations: compare with the torch port rounding the same tensors to bf16.
-    Rounding flips (fp32 arithmetic differs in the last ulp before the bf16 cast) bound the agreement
-    at ~1e-4; against the fp32 reference the mode costs ~2e-3."""
-    g, sd, batch, p = load_case("cavity_b2_gain200")
-    m = make_model(sd, p, act_dtype="bfloat16")
-    tb = {k: torch.from_numpy(v) for k, v in batch.items()}
-    with torch.no_grad():
-        got = m(tb["inputs"].cuda(), tb["case_params"].cuda(), tb["mask"].cuda())["preds"].cpu().numpy()
-    pp = opt.params_from_numpy(sd)
-    ref16 = opt.forward(pp, tb["inputs"], tb["case_params"], tb["mask"], round_fn=opt.bf16_round)["preds"].numpy()
-    e16 = rel(got, ref16)
-    e32 = rel(got, g["preds"])
-    assert e16 < 5e-4, e16
-    assert e32 < 1e-2, e32
+# bf16 activation storage: tests/test_gpu_fused.py
 
 
 def test_gradients_match_reference_golden():
