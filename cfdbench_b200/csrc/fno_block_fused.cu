@@ -20,8 +20,11 @@
 //                                                               c_ky/HW folded in, resident in TENSOR MEMORY as the A operand;
 //                                                               its (ky=0, Im) column is 1 and the matching Zt row = bias.
 //   epilogue   8 warps: TMEM -> registers -> exact-erf GELU -> bf16 -> global.
-// Warp roles (704 threads): 0-11 converters, 12-19 epilogue, 20 MMA issue (one elected lane), 21 producers (lane 0: x tiles
-// by TMA, lane 1: mode images by bulk copy).  All hand-offs are mbarriers; rings: 8 x tiles, 6 Zt operands, 4 accumulators.
+// Warp roles (768 threads): 0-11 converters, 12-19 epilogue, 20/21 tile MMA issue (even / odd tiles, one elected lane
+// each), 22 GEMM1 issue, 23 producers (lane 0: x tiles by TMA, lane 1: mode images by bulk copy).  All hand-offs are
+// mbarriers.  MMA issue is the critical path (FNO_FZ_TRACE timeline: an mbarrier wait costs the issuing thread ~300 cycles
+// even when already complete), so a tile's three inputs -- x tile, Zt operand, drained accumulator -- share ONE ring of 6
+// slots and ONE "ready" barrier (TMA bytes + 12 converter arrivals + 8 epilogue arrivals) and three threads issue.
 #include "fno_common.cuh"
 #include "tc_common.cuh"
 #include <cuda.h>
@@ -30,11 +33,16 @@
 
 namespace fno {
 
-constexpr int kFzThreads = 704;
+constexpr int kFzThreads = 768;
 constexpr int kFzConvWarps = 12, kFzEpiWarps = 8;
-constexpr int kFzMmaWarp = 20, kFzProdWarp = 21;
+constexpr int kFzMmaWarp = 20;    // 20: tiles T even, 21: tiles T odd (one elected lane each)
+constexpr int kFzG1Warp = 22;     // GEMM1 (inverse DFT along kx) issue
+constexpr int kFzProdWarp = 23;
 constexpr int kFzTilesPerUnit = 16;         // 32 rows / 2
-constexpr int kFzNX = 8, kFzNB = 6, kFzND = 4, kFzNY = 2;
+constexpr int kFzTS = 2;   // tiles per hand-off ("super-tile" = 4 image rows): every barrier wait / fence is paid once per 2 tiles
+constexpr int kFzSPU = kFzTilesPerUnit / kFzTS;   // 8 super-tiles per unit
+constexpr int kFzR = 3;    // ONE ring of super-slots for x tiles, Zt operands and accumulators: a single "ready" barrier
+constexpr int kFzNY = 3;   // mode-image stages
 constexpr uint32_t kFzXBytes = 8192;        // 2 boxes x (32 ch x 128 B)
 constexpr uint32_t kFzBtBytes = 12288;      // hi + lo, 48 rows x 128 B each
 constexpr uint32_t kFzYStage = 24576;       // (M-tile, kx parity): hi + lo, 4 ky groups x 24 rows x 128 B
@@ -46,22 +54,42 @@ constexpr size_t kYmImgBytes = 2 * kYmImgPart;
 // tensor memory columns
 constexpr uint32_t kFzColE = 0;      // E hi (48) | E lo (48)
 constexpr uint32_t kFzColD1 = 96;    // 3 x 64
-constexpr uint32_t kFzColD2 = 288;   // 4 x 32
+constexpr uint32_t kFzColD2 = 288;   // kFzR x kFzTS x 32
+
+// Optional timeline trace (tools/trace_fused.py builds a -DFNO_FZ_TRACE variant of the library): CTA 0 records
+// clock64() at the hand-off points of every role: trace[(role * 256 + T) * 8 + event].
+#ifdef FNO_FZ_TRACE
+__device__ long long* g_fz_trace = nullptr;
+#define FZ_T(role, T, ev)                                                                          \
+  do {                                                                                             \
+    if (g_fz_trace != nullptr && blockIdx.x == 0 && (T) < 256) g_fz_trace[((role) * 256 + (T)) * 8 + (ev)] = clock64(); \
+  } while (0)
+#else
+#define FZ_T(role, T, ev) do { } while (0)
+#endif
 
 struct FzSmem {
-  alignas(1024) unsigned char x[kFzNX][kFzXBytes];
-  alignas(1024) unsigned char bt[kFzNB][kFzBtBytes];
+  alignas(1024) unsigned char x[kFzR][kFzTS][kFzXBytes];
+  alignas(1024) unsigned char bt[kFzR][kFzTS][kFzBtBytes];
   alignas(1024) unsigned char y[kFzNY][kFzYStage];
   alignas(1024) unsigned char f[kFzFBytes];
   alignas(1024) unsigned char w[kFzWBytes];
   alignas(16) float bias[kC];
-  alignas(8) uint64_t x_full[kFzNX], x_empty[kFzNX];
-  uint64_t bt_full[kFzNB], bt_empty[kFzNB];
-  uint64_t d2_full[kFzND], d2_empty[kFzND];
+  // ready[s]: slot s holds tile T's x tile (1 arrival + 8 KB of TMA bytes), its Zt operand (12 converter warps) and its
+  // accumulator is free again (the 4 epilogue warps that drained it; pre-arrived once in the prologue)  -> ONE wait per tile in the MMA thread.
+  // slot_free[s]: the tile's MMAs have completed (x tile and Zt operand may be overwritten); d2_full[s]: same event,
+  // consumed by the epilogue (two barriers so that neither waiter has to re-arm the other's phase bookkeeping).
+  // Indexed by fz_bar(S) = (slot, parity of the super-tile index S): the two MMA threads / epilogue groups take alternate
+  // super-tiles, and with an odd ring size a role would otherwise see only every other phase of a slot's barrier, which
+  // the one-bit phase parity cannot express (a wait could match the completion of three super-tiles earlier).
+  alignas(8) uint64_t ready[2 * kFzR], slot_free[2 * kFzR], d2_full[2 * kFzR];
   uint64_t y_full[kFzNY], y_empty[kFzNY];
   uint64_t d1_full, d1_free, f_bar;
   uint32_t tmem_base;
 };
+__device__ __forceinline__ int fz_bar(int S) { return (S % kFzR) * 2 + (S & 1); }   // barrier of super-tile S
+__device__ __forceinline__ uint32_t fz_phase(int S) { return static_cast<uint32_t>(S / (2 * kFzR)) & 1u; }
+constexpr uint32_t kFzReadyCount = kFzConvWarps + 1 + kFzEpiWarps / 2;   // 4 epilogue warps (one group) per tile
 
 constexpr uint32_t kAMajorMN = 1u << 15, kBMajorMN = 1u << 16, kANegate = 1u << 13;
 __host__ __device__ constexpr uint32_t fz_idesc_bf16(int m, int n) {  // D f32, A/B bf16
@@ -111,6 +139,9 @@ __global__ void __launch_bounds__(kFzThreads, 1)
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   FzSmem& sm = *reinterpret_cast<FzSmem*>(smem_raw);
   if ((smem_u32(smem_raw) & 1023u) != 0) __trap();
+#ifdef FNO_FZ_TRACE
+  if (g_fz_trace != nullptr && threadIdx.x == 0) g_fz_trace[4 * 256 * 8 + blockIdx.x * 4 + 0] = clock64();
+#endif
   const int tid = threadIdx.x, lane = tid & 31, warp = tc::warp_index_uniform();
 
   const int first = blockIdx.x, stride = gridDim.x;
@@ -119,9 +150,11 @@ __global__ void __launch_bounds__(kFzThreads, 1)
 
   // ---------------------------------------------------------------- prologue (weights / constant tables only)
   if (tid == 0) {
-    for (int i = 0; i < kFzNX; ++i) { mbar_init(&sm.x_full[i], 1); mbar_init(&sm.x_empty[i], 1); }
-    for (int i = 0; i < kFzNB; ++i) { mbar_init(&sm.bt_full[i], kFzConvWarps); mbar_init(&sm.bt_empty[i], 1); }
-    for (int i = 0; i < kFzND; ++i) { mbar_init(&sm.d2_full[i], 1); mbar_init(&sm.d2_empty[i], kFzEpiWarps); }
+    for (int i = 0; i < 2 * kFzR; ++i) {
+      mbar_init(&sm.ready[i], kFzReadyCount);
+      mbar_init(&sm.slot_free[i], 1);
+      mbar_init(&sm.d2_full[i], 1);
+    }
     for (int i = 0; i < kFzNY; ++i) { mbar_init(&sm.y_full[i], 1); mbar_init(&sm.y_empty[i], 1); }
     mbar_init(&sm.d1_full, 1);
     mbar_init(&sm.d1_free, kFzConvWarps);
@@ -150,15 +183,17 @@ __global__ void __launch_bounds__(kFzThreads, 1)
   __syncthreads();
   tc::fence_after_thread_sync();
   const uint32_t tmem = sm.tmem_base;
-  if (warp >= kFzConvWarps && warp < kFzConvWarps + 4) {   // constant E operand -> tensor memory (row m in lane m)
-    const int m = (warp & 3) * 32 + lane;
-    const float* row = etab + m * 96;
+  if (warp >= kFzConvWarps && warp < kFzConvWarps + kFzEpiWarps) {
+    // constant E operand -> tensor memory (row m in lane m).  The table is stored column-major (etab[c][m]) so that a warp
+    // reads 128 contiguous bytes per column; with the row-major table every load touched 32 lines and this prologue cost
+    // 17,000 cycles per CTA (a quarter of the kernel, FNO_FZ_TRACE).  Two warps per lane quadrant, 48 columns each.
+    const int m = (warp & 3) * 32 + lane, cbase = ((warp - kFzConvWarps) >> 2) * 48;
 #pragma unroll
-    for (int c0 = 0; c0 < 96; c0 += 16) {
+    for (int c0 = 0; c0 < 48; c0 += 16) {
       float v[16];
 #pragma unroll
-      for (int j = 0; j < 16; ++j) v[j] = __ldg(row + c0 + j);
-      tc::tmem_st16(tmem + kFzColE + c0 + (static_cast<uint32_t>((warp & 3) * 32) << 16), v);
+      for (int j = 0; j < 16; ++j) v[j] = __ldg(etab + (cbase + c0 + j) * 128 + m);
+      tc::tmem_st16(tmem + kFzColE + cbase + c0 + (static_cast<uint32_t>((warp & 3) * 32) << 16), v);
     }
     tc::tmem_wait_st();
   }
@@ -166,8 +201,14 @@ __global__ void __launch_bounds__(kFzThreads, 1)
   tc::fence_before_thread_sync();
   __syncthreads();
   tc::fence_after_thread_sync();
+#ifdef FNO_FZ_TRACE
+  if (g_fz_trace != nullptr && threadIdx.x == 0) g_fz_trace[4 * 256 * 8 + blockIdx.x * 4 + 1] = clock64();
+#endif
   pdl_wait();   // ym_img and x come from the previous kernels of the chain
   pdl_launch_dependents();
+  // all accumulators start out free: the epilogue warps' share of every ready barrier's first phase
+  if (warp >= kFzConvWarps && warp < kFzConvWarps + kFzEpiWarps / 2 && lane == 0)
+    for (int S = 0; S < kFzR; ++S) mbar_arrive(&sm.ready[fz_bar(S)]);
 
   // ================================================================ converters
   if (warp < kFzConvWarps) {
@@ -182,76 +223,146 @@ __global__ void __launch_bounds__(kFzThreads, 1)
       roff[r] = k * 128 + ((((o >> 3) ^ (k & 3)) & 3) << 5) + (o & 7) * 4;
     }
     for (int k = 0; k < n_mine; ++k) {
+      if (tid == 0) FZ_T(0, k * kFzSPU, 0);
       mbar_wait(&sm.d1_full, k & 1);
       tc::fence_after_thread_sync();
+      if (tid == 0) FZ_T(0, k * kFzSPU, 1);
 #pragma unroll 1
       for (int hh = 0; hh < 2; ++hh) {
         float v[32];
         tc::tmem_ld32(tmem + kFzColD1 + mt * 64 + hh * 32 + lane_base, v);
+        if (tid == 0) FZ_T(0, k * kFzSPU + hh * 4, 2);
         if (hh == 1) {   // D1 fully read: the next unit's GEMM1 may overwrite it
           tc::fence_before_thread_sync();
           __syncwarp();
           if (lane == 0) mbar_arrive(&sm.d1_free);
         }
 #pragma unroll
-        for (int tt = 0; tt < 8; ++tt) {
-          const int T = k * kFzTilesPerUnit + hh * 8 + tt;
-          const int sb = T % kFzNB;
-          mbar_wait(&sm.bt_empty[sb], ((T / kFzNB) & 1) ^ 1);
-          unsigned char* slot = sm.bt[sb];
+        for (int s4 = 0; s4 < 4; ++s4) {
+          const int S = k * kFzSPU + hh * 4 + s4;
+          const int ss = S % kFzR;
+          if (tid == 0) FZ_T(0, S, 3);
+          if (S >= kFzR) mbar_wait(&sm.slot_free[fz_bar(S - kFzR)], fz_phase(S - kFzR));   // previous user of the slot
+          if (tid == 0) FZ_T(0, S, 4);
 #pragma unroll
-          for (int r = 0; r < 4; ++r) {
-            float z = v[tt * 4 + r];
-            if ((r & 1) && ky == 0) z = bias_o;   // Im of the ky = 0 column is dropped by C2R; the row carries the bias
-            float hi, lo;
-            tc::split_tf32(z, hi, lo);
-            *reinterpret_cast<float*>(slot + roff[r]) = hi;
-            *reinterpret_cast<float*>(slot + 6144 + roff[r]) = lo;
+          for (int i = 0; i < kFzTS; ++i) {
+            unsigned char* slot = sm.bt[ss][i];
+#pragma unroll
+            for (int r = 0; r < 4; ++r) {
+              float z = v[(s4 * kFzTS + i) * 4 + r];
+              if ((r & 1) && ky == 0) z = bias_o;   // Im of the ky = 0 column is dropped by C2R; the row carries the bias
+              float hi, lo;
+              tc::split_tf32(z, hi, lo);
+              *reinterpret_cast<float*>(slot + roff[r]) = hi;
+              *reinterpret_cast<float*>(slot + 6144 + roff[r]) = lo;
+            }
           }
           tc::fence_proxy_async_smem();
           __syncwarp();
-          if (lane == 0) mbar_arrive(&sm.bt_full[sb]);
+          if (lane == 0) mbar_arrive(&sm.ready[fz_bar(S)]);
+          if (tid == 0) FZ_T(0, S, 5);
         }
       }
     }
   }
   // ================================================================ epilogue
+  // Two groups of four warps (one warp per TMEM lane quadrant) take alternate super-tiles; a thread owns one pixel of each
+  // tile and all 32 output channels of it: one barrier wait per super-tile, one tcgen05.ld per tile, 16 independent GELU
+  // pairs per tile (the fixed latencies -- ~300 cycles per wait, ~270 per TMEM read -- dominate the epilogue otherwise).
   else if (warp < kFzConvWarps + kFzEpiWarps) {
-    const int q = warp & 3, half = (warp - kFzConvWarps) >> 2;
+    const int q = warp & 3, grp = (warp - kFzConvWarps) >> 2;
     const uint32_t lane_base = static_cast<uint32_t>(q * 32) << 16;
-    const int n_tiles = n_mine * kFzTilesPerUnit;
-    for (int T = 0; T < n_tiles; ++T) {
-      const int buf = T % kFzND;
-      const int u = unit_of(T / kFzTilesPerUnit), t = T % kFzTilesPerUnit;
-      mbar_wait(&sm.d2_full[buf], (T / kFzND) & 1);
+    const int n_super = n_mine * kFzSPU;
+    const bool odd = lane & 1;
+    for (int S = grp; S < n_super; S += 2) {
+      const int ss = S % kFzR;
+      const int u = unit_of(S / kFzSPU), t0 = (S % kFzSPU) * kFzTS;
+      if ((warp & 3) == 0 && lane == 0) FZ_T(1, S, 0);
+      mbar_wait(&sm.d2_full[fz_bar(S)], fz_phase(S));
       tc::fence_after_thread_sync();
-      float v[16];
-      fz_ld16(tmem + kFzColD2 + buf * 32 + half * 16 + lane_base, v);
-      tc::fence_before_thread_sync();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&sm.d2_empty[buf]);
-      const int b = u >> 1, px = (u & 1) * 2048 + t * 128 + q * 32 + lane;
-      __nv_bfloat16* dst = out + (static_cast<size_t>(b) * kC + half * 16) * kHW + px;
+      if ((warp & 3) == 0 && lane == 0) FZ_T(1, S, 1);
+#pragma unroll 1
+      for (int i = 0; i < kFzTS; ++i) {
+        float v[32];
+        tc::tmem_ld32(tmem + kFzColD2 + (ss * kFzTS + i) * 32 + lane_base, v);
+        if (i == kFzTS - 1) {   // both accumulators of the slot are in registers: the slot may be reused
+          tc::fence_before_thread_sync();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&sm.ready[fz_bar(S + kFzR)]);   // next user of the slot
+          if ((warp & 3) == 0 && lane == 0) FZ_T(1, S, 2);
+        }
+        // lanes 2i / 2i+1 hold adjacent pixels: exchange halves so that the even lane stores the pixel PAIR of channel c
+        // and the odd lane the pair of channel c+1 (one 4-byte store per two values instead of two 2-byte stores)
+        const int b = u >> 1, px = (u & 1) * 2048 + (t0 + i) * 128 + q * 32 + (lane & ~1);
+        __nv_bfloat16* dst = out + (static_cast<size_t>(b) * kC + (odd ? 1 : 0)) * kHW + px;
 #pragma unroll
-      for (int c = 0; c < 16; c += 2) {
-        const float2 g = gelu_erf2(make_float2(v[c], v[c + 1]));
-        dst[static_cast<size_t>(c) * kHW] = __float2bfloat16_rn(g.x);
-        dst[static_cast<size_t>(c + 1) * kHW] = __float2bfloat16_rn(g.y);
+        for (int c = 0; c < 32; c += 2) {
+          const float2 g = gelu_erf2(make_float2(v[c], v[c + 1]));
+          const __nv_bfloat162 pk = __float22bfloat162_rn(g);                    // (channel c, channel c+1) of my pixel
+          const uint32_t mine = *reinterpret_cast<const uint32_t*>(&pk);
+          const uint32_t other = __shfl_xor_sync(0xffffffffu, mine, 1);
+          // even lane: (my c, neighbour's c);  odd lane: (neighbour's c+1, my c+1)
+          const uint32_t pair = odd ? __byte_perm(other, mine, 0x7632) : __byte_perm(mine, other, 0x5410);
+          *reinterpret_cast<uint32_t*>(dst + static_cast<size_t>(c) * kHW) = pair;
+        }
       }
+      if ((warp & 3) == 0 && lane == 0) FZ_T(1, S, 3);
     }
   }
-  // ================================================================ MMA issue
-  else if (warp == kFzMmaWarp) {
+  // ================================================================ MMA issue: tiles
+  // Two issuing threads (warps 20 / 21) take alternate super-tiles: the ready-wait costs ~300 cycles even when complete,
+  // so one thread alone could not keep the tensor pipe (~620 cycles per tile) fed.  Each thread commits only its own
+  // super-tile's barriers (tcgen05.commit tracks the MMAs of the executing thread).
+  else if (warp == kFzMmaWarp || warp == kFzMmaWarp + 1) {
     if (tc::elect_one()) {
-      const uint32_t f_hi = tc::smem_addr(sm.f), f_lo = f_hi + kFzFBytes / 2;
       const uint32_t w_s = tc::smem_addr(sm.w);
-      constexpr uint32_t idesc_g1 = tc::make_idesc_tf32(128, 64) | kAMajorMN;
       constexpr uint32_t idesc_e = tc::make_idesc_tf32(128, 32) | kBMajorMN;
       constexpr uint32_t idesc_c = fz_idesc_bf16(128, 32) | kAMajorMN;
-
-      auto issue_gemm1 = [&](int k) {
+      const int n_super = n_mine * kFzSPU;
+#pragma unroll 1
+      for (int S = warp - kFzMmaWarp; S < n_super; S += 2) {
+        const int ss = S % kFzR;
+        FZ_T(2, S, 0);
+        mbar_wait(&sm.ready[fz_bar(S)], fz_phase(S));   // x tiles landed, Zt operands written, accumulators drained
+        tc::fence_after_thread_sync();
+        FZ_T(2, S, 2);
+#pragma unroll
+        for (int i = 0; i < kFzTS; ++i) {
+          const uint32_t d = tmem + kFzColD2 + (ss * kFzTS + i) * 32;
+          const uint32_t x_s = tc::smem_addr(sm.x[ss][i]);
+#pragma unroll
+          for (int pc = 0; pc < 3; ++pc)
+#pragma unroll
+            for (int ks = 0; ks < 2; ++ks)
+              fz_mma_f16_ss(d, fz_desc_sw128(x_s + ks * 2048, 4096, 1024),
+                            tc::make_smem_desc(w_s + pc * 2048 + ks * 1024, 512, 128), idesc_c, (pc | ks) ? 1u : 0u);
+          const uint32_t z_hi = tc::smem_addr(sm.bt[ss][i]), z_lo = z_hi + 6144;
+#pragma unroll
+          for (int pass = 0; pass < 3; ++pass) {
+            const uint32_t a_t = tmem + kFzColE + ((pass == 1) ? 48u : 0u);
+            const uint32_t b_s = (pass == 2) ? z_lo : z_hi;
+#pragma unroll
+            for (int ks = 0; ks < 6; ++ks)
+              fz_mma_tf32_ts(d, a_t + ks * 8, fz_desc_sw128_32(b_s + ks * 1024, 0, 512), idesc_e, 1u);
+          }
+        }
+        tc::mma_commit(&sm.slot_free[fz_bar(S)]);
+        tc::mma_commit(&sm.d2_full[fz_bar(S)]);
+        FZ_T(2, S, 5);
+      }
+    }
+    __syncwarp();
+  }
+  // ================================================================ MMA issue: GEMM1 (its own thread: a 24 KB stage load
+  // takes ~1300 cycles from DRAM, which must not hold up the tile MMAs; the tensor pipe interleaves the two streams)
+  else if (warp == kFzG1Warp) {
+    if (tc::elect_one()) {
+      const uint32_t f_hi = tc::smem_addr(sm.f), f_lo = f_hi + kFzFBytes / 2;
+      constexpr uint32_t idesc_g1 = tc::make_idesc_tf32(128, 64) | kAMajorMN;
+#pragma unroll 1
+      for (int k = 0; k < n_mine; ++k) {
         const uint32_t neg = (unit_of(k) & 1) ? kANegate : 0u;   // second half image: odd kx change sign
-        if (k >= 1) {
+        if (k >= 1) {   // the converters have pulled the previous unit's D1 out of tensor memory (at their tile 8)
           mbar_wait(&sm.d1_free, (k - 1) & 1);
           tc::fence_after_thread_sync();
         }
@@ -259,8 +370,10 @@ __global__ void __launch_bounds__(kFzThreads, 1)
         for (int st = 0; st < 6; ++st) {
           const int c = k * 6 + st, slot = c % kFzNY;
           const int mt = st >> 1, par = st & 1;
+          FZ_T(3, k * 8 + st, 0);
           mbar_wait(&sm.y_full[slot], (c / kFzNY) & 1);
           tc::fence_after_thread_sync();
+          FZ_T(3, k * 8 + st, 1);
           const uint32_t a_hi = tc::smem_addr(sm.y[slot]), a_lo = a_hi + kFzYStage / 2;
           const uint32_t d = tmem + kFzColD1 + mt * 64;
           const uint32_t idesc = idesc_g1 | (par ? neg : 0u);
@@ -276,59 +389,30 @@ __global__ void __launch_bounds__(kFzThreads, 1)
             }
           }
           tc::mma_commit(&sm.y_empty[slot]);
+          FZ_T(3, k * 8 + st, 2);
         }
         tc::mma_commit(&sm.d1_full);
-      };
-
-      if (n_mine > 0) issue_gemm1(0);
-      for (int k = 0; k < n_mine; ++k) {
-#pragma unroll 1
-        for (int t = 0; t < kFzTilesPerUnit; ++t) {
-          if (t == 8 && k + 1 < n_mine) issue_gemm1(k + 1);
-          const int T = k * kFzTilesPerUnit + t;
-          const int sx = T % kFzNX, sb = T % kFzNB, buf = T % kFzND;
-          const uint32_t d = tmem + kFzColD2 + buf * 32;
-          mbar_wait(&sm.x_full[sx], (T / kFzNX) & 1);
-          mbar_wait(&sm.d2_empty[buf], ((T / kFzND) & 1) ^ 1);
-          tc::fence_after_thread_sync();
-          const uint32_t x_s = tc::smem_addr(sm.x[sx]);
-#pragma unroll
-          for (int pc = 0; pc < 3; ++pc)
-#pragma unroll
-            for (int ks = 0; ks < 2; ++ks)
-              fz_mma_f16_ss(d, fz_desc_sw128(x_s + ks * 2048, 4096, 1024),
-                            tc::make_smem_desc(w_s + pc * 2048 + ks * 1024, 512, 128), idesc_c, (pc | ks) ? 1u : 0u);
-          tc::mma_commit(&sm.x_empty[sx]);
-          mbar_wait(&sm.bt_full[sb], (T / kFzNB) & 1);
-          tc::fence_after_thread_sync();
-          const uint32_t z_hi = tc::smem_addr(sm.bt[sb]), z_lo = z_hi + 6144;
-#pragma unroll
-          for (int pass = 0; pass < 3; ++pass) {
-            const uint32_t a_t = tmem + kFzColE + ((pass == 1) ? 48u : 0u);
-            const uint32_t b_s = (pass == 2) ? z_lo : z_hi;
-#pragma unroll
-            for (int ks = 0; ks < 6; ++ks)
-              fz_mma_tf32_ts(d, a_t + ks * 8, fz_desc_sw128_32(b_s + ks * 1024, 0, 512), idesc_e, 1u);
-          }
-          tc::mma_commit(&sm.bt_empty[sb]);
-          tc::mma_commit(&sm.d2_full[buf]);
-        }
       }
     }
     __syncwarp();
   }
   // ================================================================ producers
   else if (warp == kFzProdWarp) {
-    if (lane == 0) {          // x tiles: two {64 px, 32 ch} boxes per tile
-      const int n_tiles = n_mine * kFzTilesPerUnit;
-      for (int T = 0; T < n_tiles; ++T) {
-        const int sx = T % kFzNX;
-        const int u = unit_of(T / kFzTilesPerUnit), t = T % kFzTilesPerUnit;
-        const int b = u >> 1, px0 = (u & 1) * 2048 + t * 128;
-        mbar_wait(&sm.x_empty[sx], ((T / kFzNX) & 1) ^ 1);
-        mbar_expect_tx(&sm.x_full[sx], kFzXBytes);
-        fz_tma_load_2d(sm.x[sx], &x_map, px0, b * kC, &sm.x_full[sx]);
-        fz_tma_load_2d(sm.x[sx] + 4096, &x_map, px0 + 64, b * kC, &sm.x_full[sx]);
+    if (lane == 0) {          // x tiles: two {64 px, 32 ch} boxes per tile, kFzTS tiles per super-slot
+      const int n_super = n_mine * kFzSPU;
+      for (int S = 0; S < n_super; ++S) {
+        const int ss = S % kFzR;
+        const int u = unit_of(S / kFzSPU), t0 = (S % kFzSPU) * kFzTS;
+        const int b = u >> 1;
+        if (S >= kFzR) mbar_wait(&sm.slot_free[fz_bar(S - kFzR)], fz_phase(S - kFzR));
+        uint64_t* rdy = &sm.ready[fz_bar(S)];
+        mbar_expect_tx(rdy, kFzTS * kFzXBytes);
+#pragma unroll
+        for (int i = 0; i < kFzTS; ++i) {
+          const int px0 = (u & 1) * 2048 + (t0 + i) * 128;
+          fz_tma_load_2d(sm.x[ss][i], &x_map, px0, b * kC, rdy);
+          fz_tma_load_2d(sm.x[ss][i] + 4096, &x_map, px0 + 64, b * kC, rdy);
+        }
       }
     } else if (lane == 1) {   // mode images: per (M-tile, kx parity) 8 runs of 24 rows x 128 B
       for (int k = 0; k < n_mine; ++k) {
@@ -352,12 +436,15 @@ __global__ void __launch_bounds__(kFzThreads, 1)
 
   tc::fence_before_thread_sync();
   __syncthreads();
+#ifdef FNO_FZ_TRACE
+  if (g_fz_trace != nullptr && threadIdx.x == 0) g_fz_trace[4 * 256 * 8 + blockIdx.x * 4 + 2] = clock64();
+#endif
   if (warp == kFzMmaWarp) tc::tmem_dealloc<512>(tmem);
 }
 
 // ------------------------------------------------------------------------------------------------
 // Constant tables, built once per device in float64 and split into tf32 hi/lo (round to nearest).
-//   etab[m][96]: row m = 64 j + w of the A operand (E (+) E): columns 0..47 hi, 48..95 lo; column k = 24 j' + 2 ky + ri:
+//   etab[96][128] (column-major): row m = 64 j + w of the A operand (E (+) E): columns 0..47 hi, 48..95 lo; column k = 24 j' + 2 ky + ri:
 //                c_ky/4096 * cos(2 pi ky w/64) (ri = 0), -c_ky/4096 * sin(..) (ri = 1), 0 for j != j';
 //                the (ky = 0, ri = 1) column is 1 (bias row of the B operand).   c_0 = 1, c_ky = 2 (Hermitian fold).
 //   ftab: B operand of GEMM1, [n = 2 h' + ri (64)][k = 24 p + 2 q + ri' (48)], kxi = 2 q + p, kx = kxi (< 12) or kxi + 40:
@@ -396,8 +483,8 @@ static cudaError_t fz_ensure(int dev, cudaStream_t stream) {
         val = ri == 0 ? c * cos(ang) : (ky == 0 ? 1.0 : -c * sin(ang));
       }
       const float hi = fz_round_tf32_host(val);
-      h_e[m * 96 + k] = hi;
-      h_e[m * 96 + 48 + k] = fz_round_tf32_host(val - static_cast<double>(hi));
+      h_e[k * 128 + m] = hi;                                                        // column-major: [column][row]
+      h_e[(48 + k) * 128 + m] = fz_round_tf32_host(val - static_cast<double>(hi));
     }
   }
   for (int n = 0; n < 64; ++n) {
@@ -453,6 +540,13 @@ static cudaError_t fz_make_map(const void* act, int batch, CUtensorMap* out) {
                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS ? cudaSuccess : cudaErrorInvalidValue;
 }
+
+#ifdef FNO_FZ_TRACE
+extern "C" int fno_debug_fused_trace(void* p) {
+  long long* q = static_cast<long long*>(p);
+  return cudaMemcpyToSymbol(g_fz_trace, &q, sizeof(q)) == cudaSuccess ? 0 : 2;
+}
+#endif
 
 size_t ym_image_bytes(int batch) { return static_cast<size_t>(batch) * kYmImgBytes; }
 

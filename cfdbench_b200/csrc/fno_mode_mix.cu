@@ -82,6 +82,15 @@ __device__ __forceinline__ void mx_split_store(const MxRegs& r, float* a_hi, flo
   }
 }
 
+// 256-bit global store (sm_100: st.global.v8): the image epilogue writes 32-byte chunks of 32 different samples per warp
+// instruction, so the instruction count -- not the bytes -- is what the LSU queue sees (lg_throttle 5.0 per issue with
+// 16-byte stores, profiles/ncu_r02*.md).
+__device__ __forceinline__ void mx_store32(void* dst, const float* v) {
+  asm volatile("st.global.v8.f32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(dst), "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]),
+               "f"(v[4]), "f"(v[5]), "f"(v[6]), "f"(v[7])
+               : "memory");
+}
+
 template <int GRP>
 __device__ __forceinline__ void mx_group_barrier() {
   asm volatile("bar.sync %0, %1;" ::"n"(GRP + 1), "n"(kMxGroup) : "memory");
@@ -132,10 +141,8 @@ __device__ __forceinline__ void mx_pipeline(MxSmem& sm, const float4* __restrict
 #pragma unroll
           for (int j = 0; j < 8; ++j) tc::split_tf32(v[2 * (8 * c + j) + ri], hi[j], lo[j]);
           unsigned char* dst = img + row * 128 + (((2 * half + c) ^ (row & 3)) << 5);
-          reinterpret_cast<float4*>(dst)[0] = make_float4(hi[0], hi[1], hi[2], hi[3]);
-          reinterpret_cast<float4*>(dst)[1] = make_float4(hi[4], hi[5], hi[6], hi[7]);
-          reinterpret_cast<float4*>(dst + 73728)[0] = make_float4(lo[0], lo[1], lo[2], lo[3]);
-          reinterpret_cast<float4*>(dst + 73728)[1] = make_float4(lo[4], lo[5], lo[6], lo[7]);
+          mx_store32(dst, hi);            // one 32-byte chunk = one full sector per store instruction
+          mx_store32(dst + 73728, lo);
         }
       }
     }
