@@ -110,8 +110,8 @@ class Anything:
     def __exit__(self, *exc):
         return False
 
-    def __mro_entries__(self, bases):  # `class X(stub.Base)` in files the FNO path never runs
-        return (object,)
+    def __mro_entries__(self, bases):  # `class X(stub.A, stub.B)` in files the FNO path never runs: distinct dummy bases
+        return (type("StubBase", (), {"__init__": lambda self, *a, **k: None}),)
 
     def __bool__(self):
         return False

@@ -7,10 +7,10 @@ What it does (no file of the reference is edited; SURVEY.md 3.1 lists why each s
      (test_multistep.py:109 checks isinstance against it) -- `cfdbench_b200.base_model` picks it up;
   2. rebinds `models.fno.fno2d.Fno2d` to `cfdbench_b200.Fno2d` BEFORE `utils.autoregressive` imports it
      (utils/autoregressive.py:10 is the plug-in seam);
-  3. optionally provides import stubs for third-party packages that only the fork's diffusion/VAE code
-     needs (diffusers, sklearn, seaborn, accelerate, matplotlib) when they are not installed
-     (`--stub-missing`), and injects `Args.lr_step_size` which train_auto.py:357 reads but args.py
-     never declares (defect 1);
+  3. optionally (`--stub-missing`) provides stand-ins for packages that are NOT installed: `tap.Tap` (a minimal
+     typed-argument-parser, cfdbench_b200/_stubs.py) and no-op modules for what only the fork's plotting / diffusion /
+     VAE code needs (matplotlib, diffusers, sklearn, seaborn, accelerate, ...), and injects `Args.lr_step_size` which
+     train_auto.py:357 reads but args.py never declares (defect 1);
   4. runs the script as `__main__`.
 """
 from __future__ import annotations
@@ -28,15 +28,8 @@ STUBBABLE = ("diffusers", "sklearn", "seaborn", "accelerate", "matplotlib", "h5p
 
 class _StubLoader(importlib.abc.Loader):
     def create_module(self, spec):
-        m = types.ModuleType(spec.name)
-        m.__path__ = []  # behave like a package so submodule imports resolve to further stubs
-
-        def _getattr(name):
-            if name.startswith("__"):
-                raise AttributeError(name)
-            return type(name, (), {"__init__": lambda self, *a, **k: None, "__call__": lambda self, *a, **k: None})
-        m.__getattr__ = _getattr
-        return m
+        from ._stubs import make_stub_module
+        return make_stub_module(spec.name)
 
     def exec_module(self, module):
         pass
@@ -71,6 +64,8 @@ def install(src_dir: str, stub_missing: bool = False, act_dtype: str | None = No
         sys.path.insert(0, src_dir)
     sys.dont_write_bytecode = True
     if stub_missing:
+        from ._stubs import install_tap
+        install_tap()   # `tap.Tap` (reference args.py:1) when typed-argument-parser is not installed
         gone = missing()
         if gone:
             sys.meta_path.append(_StubFinder(gone))

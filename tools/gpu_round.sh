@@ -1,13 +1,15 @@
 #!/bin/bash
 # One GPU session: parity tests, bench, ncu launch list + full captures of named kernels.
 # Usage (under gpurun): bash tools/gpu_round.sh <tag> [kernel_regex:skip ...]
-TAG=${1:-r01}; shift
+TAG=${1:-r02}; shift
 mkdir -p gpurun_out
-timeout 600 python -m pytest tests -m gpu -q --tb=short -p no:cacheprovider --timeout 120 > gpurun_out/pytest_gpu_$TAG.log 2>&1
-echo "pytest exit $?"; tail -4 gpurun_out/pytest_gpu_$TAG.log | cut -c1-300
+timeout 900 python -m pytest tests -m gpu -q --tb=short -p no:cacheprovider --timeout 300 > gpurun_out/pytest_gpu_$TAG.log 2>&1
+echo "pytest exit $?"; tail -6 gpurun_out/pytest_gpu_$TAG.log | cut -c1-300
 timeout 600 python bench.py --steps 20 --warmup 3 > gpurun_out/bench_$TAG.json 2> gpurun_out/bench_$TAG.err
-echo "bench exit $?"; tail -c 1500 gpurun_out/bench_$TAG.json; tail -3 gpurun_out/bench_$TAG.err
-timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 90 --csv \
+echo "bench exit $?"; python -c "
+import json; d=json.loads(open('gpurun_out/bench_$TAG.json').read().strip().splitlines()[-1])
+print({k: d[k] for k in ('value','ms_per_step','ms_per_step_min','e2e','gpu_launches')}); print({k: round(v['mean_us'],1) for k,v in d['kernels'].items()}); print(d['roofline']); print(d.get('cpu_baseline'))"; tail -3 gpurun_out/bench_$TAG.err
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 120 --csv \
    --log-file gpurun_out/launches_$TAG.csv python tools/prof_driver.py --act bf16 --steps 3 > /dev/null 2>&1
 echo "ncu launches exit $?"; grep -c gpu__time gpurun_out/launches_$TAG.csv
 for KS in "$@"; do
@@ -16,4 +18,4 @@ for KS in "$@"; do
      -o gpurun_out/prof_${K}_$TAG python tools/prof_driver.py --act bf16 --steps 2 > gpurun_out/ncu_${K}_$TAG.log 2>&1
   echo "ncu $K exit $?"
 done
-ls -la gpurun_out | tail -12
+ls -la gpurun_out | tail -8

@@ -18,7 +18,11 @@ out.append(f"bench.py --steps {bench['steps']} --warmup {bench['warmup']} (B200,
            f"train step {bench['train_step']['ms_per_step']:.2f} ms; clocks {bench['clocks']}.")
 out.append("\n## per-kernel CUDA-event times inside bench.py (us, bf16 | fp32)")
 for n, v in bench["kernels"].items():
-    out.append(f"- {n}: {v['mean_us']:.1f} | {fp['kernels'][n]['mean_us']:.1f}  (x{v['launches_per_step']} per step)")
+    other = fp.get("kernels", {}).get(n, {}).get("mean_us")
+    out.append(f"- {n}: {v['mean_us']:.1f} | {other if other is None else round(other, 1)}  (x{v['launches_per_step']} per step)")
+for n, v in fp.get("kernels", {}).items():
+    if n not in bench["kernels"]:
+        out.append(f"- {n}: - | {v['mean_us']:.1f}  (fp32-storage path only, x{v['launches_per_step']} per step)")
 rf = bench["roofline"]
 out.append(f"\nroofline (bench.py): {rf}")
 # launch list
@@ -64,8 +68,15 @@ for rep in sorted(glob.glob(os.path.join(go, f"prof_*_{tag}.ncu-rep"))):
         x, u = float(v[h.index(metric)].replace(",", "")), units[h.index(metric)]
         return x * {"Mbyte": 1e6, "Kbyte": 1e3, "Gbyte": 1e9, "byte": 1}[u]
     t = mb("dram__bytes_read.sum") + mb("dram__bytes_write.sum")
-    traffic[name.split("(")[0]] = int(t)
+    short = name.split("(")[0].split("<")[0].replace("void ", "").split("::")[-1].strip()
+    traffic[short] = (int(t), os.path.basename(rep))
     out.append(f"- DRAM traffic (read+write): {t / 1e6:.1f} Mbyte")
-out.append(f"\nDRAM traffic per launch (bytes): {traffic}")
+out.append(f"\nDRAM traffic per launch (bytes): { {k: v[0] for k, v in traffic.items()} }")
+# bench.py reads roofline.traffic from here (keyed by kernel | activation storage | batch of the capture)
+tj = os.path.join(pr, "ncu_traffic.json")
+table = json.load(open(tj)) if os.path.exists(tj) else {}
+for k, (t, rep) in traffic.items():
+    table[f"{k}|bf16|256"] = {"dram_bytes": t, "source": f"ncu --set full, {rep}, tools/prof_driver.py --act bf16 (B=256), tag {tag}"}
+json.dump(table, open(tj, "w"), indent=1, sort_keys=True)
 open(os.path.join(pr, f"ncu_{tag}.md"), "w").write("\n".join(out) + "\n")
 print("\n".join(out))
