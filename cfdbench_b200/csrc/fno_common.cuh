@@ -202,6 +202,40 @@ __device__ __forceinline__ float2 gelu_erf2(float2 x) {
   return __ffma2_rn(make_float2(-a.x, -a.y), h, make_float2(fmaxf(x.x, 0.f), fmaxf(x.y, 0.f)));
 }
 
+// Degree-5 variant of the packed GELU for the project kernel in bf16 storage mode (project_ws_kernel), whose epilogue -- 134 M
+// GELUs per launch at B=256 -- is bound by the fma pipe: a 3-register FFMA2 occupies it for 4 cycles, an immediate-operand
+// one for 2, and neither warp specialisation nor more instruction-level parallelism changed its 85 us (profiles/README.md).
+// q(a) ~ log2(erfc(a/sqrt2)/2), weighted minimax fit of the GELU error on [0, 8], negative leading coefficient (2^q underflows
+// beyond the fit range, no clamp).  fp32 result within 6.4e-7 abs of the float64 GELU -- torch's own fp32 nn.GELU() is at
+// 1.3e-6 -- checked by tests/test_host.py.  Used ONLY where the output is not fed back through further layers in fp32
+// parity mode: with it everywhere the fp32-storage rel-L2 against the reference rose from 2.2e-7 to 2.1e-6 (measured), so
+// the Fourier blocks and the fp32-storage project keep the degree-8 fit above.
+#define FNO_GELU_E0 -1.0000376366992503f
+#define FNO_GELU_E1 -1.1507877474081256f
+#define FNO_GELU_E2 -0.45999268192636272f
+#define FNO_GELU_E3 -0.051827144796875543f
+#define FNO_GELU_E4 0.0070844550401877602f
+#define FNO_GELU_E5 -0.00047329356073930895f
+// N pairs at once, coefficient loop outside (N independent Horner chains)
+template <int N>
+__device__ __forceinline__ void gelu_erf2_deg5_batch(float2 (&x)[N]) {
+  float2 p[N];
+  constexpr float kE[6] = {FNO_GELU_E0, FNO_GELU_E1, FNO_GELU_E2, FNO_GELU_E3, FNO_GELU_E4, FNO_GELU_E5};
+#pragma unroll
+  for (int i = 0; i < N; ++i)
+    p[i] = __ffma2_rn(make_float2(kE[5], kE[5]), make_float2(fabsf(x[i].x), fabsf(x[i].y)), make_float2(kE[4], kE[4]));
+#pragma unroll
+  for (int k = 3; k >= 0; --k)
+#pragma unroll
+    for (int i = 0; i < N; ++i)
+      p[i] = __ffma2_rn(p[i], make_float2(fabsf(x[i].x), fabsf(x[i].y)), make_float2(kE[k], kE[k]));
+#pragma unroll
+  for (int i = 0; i < N; ++i) p[i] = make_float2(ex2_approx(p[i].x), ex2_approx(p[i].y));   // erfc(|x|/sqrt2) / 2
+#pragma unroll
+  for (int i = 0; i < N; ++i)
+    x[i] = __ffma2_rn(make_float2(-fabsf(x[i].x), -fabsf(x[i].y)), p[i], make_float2(fmaxf(x[i].x, 0.f), fmaxf(x[i].y, 0.f)));
+}
+
 // status codes of the C ABI
 enum : int { kOk = 0, kErrArg = 1, kErrCuda = 2, kErrUnsupported = 3 };
 

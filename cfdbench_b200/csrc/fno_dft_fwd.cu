@@ -12,6 +12,7 @@
 // j is warp-uniform so the four codelets do not diverge.  X[64-kx', ky] = conj(F[kx'][-ky]).
 #include "fft_codelets.cuh"
 #include "fno_common.cuh"
+#include <stdlib.h>
 
 namespace fno {
 
@@ -71,8 +72,8 @@ __device__ __forceinline__ void row_transform_and_emit(const float2* __restrict_
   }
 }
 
-template <typename TAct>
-__global__ void __launch_bounds__(kDftThreads, 4)
+template <typename TAct, int MINB>
+__global__ void __launch_bounds__(kDftThreads, MINB)
     dft_fwd_kernel(const TAct* __restrict__ x, float2* __restrict__ xm, float s0, float s1) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   DftSmem<TAct>& sm = *reinterpret_cast<DftSmem<TAct>*>(smem_raw);
@@ -133,7 +134,13 @@ __global__ void __launch_bounds__(kDftThreads, 4)
 
 template <typename TAct>
 cudaError_t launch_dft_fwd(const void* x, void* xm, int batch, float s0, float s1, cudaStream_t stream) {
-  auto kern = dft_fwd_kernel<TAct>;
+  static int minb = 0;
+  if (minb == 0) {
+    const char* ev = getenv("FNO_DFT_MINB");   // experiment knob: resident CTAs per SM the kernel is compiled for
+    minb = ev ? atoi(ev) : 4;
+    if (minb < 4 || minb > 6) minb = 4;
+  }
+  auto kern = minb == 4 ? dft_fwd_kernel<TAct, 4> : (minb == 5 ? dft_fwd_kernel<TAct, 5> : dft_fwd_kernel<TAct, 6>);
   constexpr size_t smem = sizeof(DftSmem<TAct>);
   static bool configured = false;  // per-instantiation
   if (!configured) {

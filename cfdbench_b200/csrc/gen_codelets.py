@@ -404,19 +404,60 @@ def fmt_const(c: float) -> str:
 
 
 def emit(name, signature, outs, doc):
+    """Straight-line code.  A constant multiple used exactly once, by an add or a sub, is fused into it:
+    `fno_fma(c, a, x)` = c*a + x and `fno_fms(c, a, x)` = c*a - x  (x - c*a becomes fno_fma(-c, a, x)).  For scalar T the
+    compiler would contract these anyway; spelling them out lets a packed two-lane type (f32x2 in fno_dft_fwd.cu) map
+    every fused pair onto ONE FFMA2 instead of FMUL2 + FADD2."""
     order = needed(outs)
-    lines = [f"// {doc}", f"// ops: {op_counts(outs)}",
+    uses, addsub_uses = {}, {}
+    for n in order:
+        for opnd in (n.a, n.b):
+            if isinstance(opnd, Node):
+                uses[opnd.id] = uses.get(opnd.id, 0) + 1
+                if n.op in ("add", "sub"):
+                    addsub_uses[opnd.id] = addsub_uses.get(opnd.id, 0) + 1
+    for _, n in outs:
+        if n is not None:
+            uses[n.id] = uses.get(n.id, 0) + 1
+    # a multiply whose every consumer is an add / sub can be folded into each of them (a +- c*t butterflies: two FMAs
+    # instead of one multiply and two adds); a consumer can absorb only one of its operands
+    cand = lambda m: isinstance(m, Node) and m.op == "mul" and uses.get(m.id, 0) == addsub_uses.get(m.id, 0)  # noqa: E731
+    choice, chosen = {}, {}
+    for n in order:
+        if n.op in ("add", "sub"):
+            pick = n.b if cand(n.b) else (n.a if cand(n.a) else None)
+            if pick is not None:
+                choice[n.id] = pick.id
+                chosen[pick.id] = chosen.get(pick.id, 0) + 1
+    fused = {mid for mid, k in chosen.items() if k == uses[mid]}   # muls that need no instruction of their own
+    for nid in list(choice):   # consumers of a mul that must be emitted anyway use it directly
+        if choice[nid] not in fused:
+            del choice[nid]
+    cnt = op_counts(outs)
+    n_fma = len(choice)
+    total = cnt["add"] + cnt["sub"] + cnt["mul"] + cnt["neg"] - len(fused)
+    lines = [f"// {doc}", f"// ops: {cnt}; emitted: {total} instructions, {n_fma} of them fma ({len(fused)} multiplies folded)",
              "template <typename T>", f"FNO_HD void {name}({signature}) {{"]
     ref = {}
     for n in order:
         if n.op == "in":
             ref[n.id] = n.name
             continue
+        if n.op == "mul" and n.id in fused:
+            continue
         v = f"t{n.id}"
-        if n.op == "add":
-            e = f"{ref[n.a.id]} + {ref[n.b.id]}"
-        elif n.op == "sub":
-            e = f"{ref[n.a.id]} - {ref[n.b.id]}"
+        if n.op in ("add", "sub"):
+            a, b = n.a, n.b
+            if choice.get(n.id) == b.id:
+                # x + c*t  /  x - c*t
+                c = b.c if n.op == "add" else -b.c
+                e = f"fno_fma({fmt_const(c)}, {ref[b.a.id]}, {ref[a.id]})"
+            elif choice.get(n.id) == a.id:
+                # c*t + y  /  c*t - y
+                e = (f"fno_fma({fmt_const(a.c)}, {ref[a.a.id]}, {ref[b.id]})" if n.op == "add"
+                     else f"fno_fms({fmt_const(a.c)}, {ref[a.a.id]}, {ref[b.id]})")
+            else:
+                e = f"{ref[a.id]} {'+' if n.op == 'add' else '-'} {ref[b.id]}"
         elif n.op == "mul":
             e = f"{fmt_const(n.c)} * {ref[n.a.id]}"
         else:
@@ -522,6 +563,13 @@ HEADER = '''// GENERATED by gen_codelets.py -- do not edit.  Pruned 64-point DFT
 #endif
 
 namespace fno_codelets {
+
+// c*a + x and c*a - x.  Scalar types: plain expressions (the compiler contracts them to one FMA).  A packed two-lane type
+// provides its own overloads (found by argument-dependent lookup), e.g. f32x2 in fno_dft_fwd.cu -> one FFMA2.
+template <typename T>
+FNO_HD T fno_fma(T c, T a, T x) { return c * a + x; }
+template <typename T>
+FNO_HD T fno_fms(T c, T a, T x) { return c * a - x; }
 
 '''
 

@@ -183,6 +183,29 @@ def test_block_fused_equals_unfused_path(lib):
     assert np.all(np.abs(a - b) <= 1.0001 * bf16_ulp(a) + 2e-5)
 
 
+@pytest.mark.parametrize("batch,problem", [(1, "cavity"), (5, "cylinder"), (40, "cavity")])
+def test_project_ws_kernel_bf16(lib, batch, problem):
+    """fc1 + GELU + fc2 + mask on bf16 activations (project_ws_kernel: TMA-fed kind::f16 MMAs, W1 / b1 as three bf16
+    pieces): the inputs are bf16-exact, so the comparison with the float64 oracle measures the arithmetic only.
+    40 samples = 1280 tiles > 148 CTAs x 4 slots: every ring slot wraps several times."""
+    from cfdbench_b200 import _lib
+    p = synth.n_case_params(problem)
+    sd = synth.make_state_dict(5, n_params=p)
+    m = make_model(sd, p, act_dtype="bfloat16")
+    pk = m._pack()
+    rng = np.random.default_rng(7 + batch)
+    a = torch.from_numpy(rng.standard_normal((batch, 32, 64, 64)).astype(np.float32)).to(torch.bfloat16)
+    mk = synth.make_batch(6, batch, problem, with_label=False)["mask"]
+    a_d, mk_d = a.cuda(), dev(mk)
+    preds = torch.zeros(batch, 2, 64, 64, device="cuda")
+    _lib.check(lib.fno_project_fwd(a_d.data_ptr(), mk_d.data_ptr(), C.byref(pk["struct"]), preds.data_ptr(), batch,
+                                   _lib.ACT_BF16, stream()), "project")
+    z1 = onp.conv1x1(a.float().numpy().astype(np.float64), sd["fc1.weight"], sd["fc1.bias"])
+    ref = onp.conv1x1(onp.gelu(z1), sd["fc2.weight"], sd["fc2.bias"]) * mk
+    assert rel(preds.cpu().numpy(), ref) < 3e-6
+    assert float(np.abs(preds.cpu().numpy() * (1 - mk)).max()) == 0.0
+
+
 # ------------------------------------------------------------------------------ whole model, bf16 storage
 
 def _bf16_oracle_forward(sd, batch):

@@ -236,6 +236,27 @@ def test_device_gelu_polynomial_in_float32():
     assert np.sqrt(np.mean((g2 - ref) ** 2)) < 1.5e-7
 
 
+def test_device_gelu_degree5_variant_in_float32():
+    """gelu_erf2_deg5_batch (project kernel, bf16 storage): degree-5 fit, max abs error below torch's own fp32 GELU."""
+    from math import erf
+    src = open(os.path.join(ROOT, "cfdbench_b200", "csrc", "fno_common.cuh")).read()
+    eco = [np.float32(float(re.search(rf"#define FNO_GELU_E{i} (\S+)f", src).group(1))) for i in range(6)]
+    xw = np.linspace(-40, 40, 800001).astype(np.float32)   # well beyond the fit range [0, 8]: the tail must underflow
+    aw = np.abs(xw)
+    q = np.full_like(aw, eco[5])
+    for c in eco[4::-1]:
+        q = (q * aw + c).astype(np.float32)
+    assert np.all(np.diff(q[xw >= 0]) < 0)  # monotone decreasing: 2^q underflows, no clamp needed
+    h = np.exp2(q.astype(np.float64)).astype(np.float32)
+    g = (np.maximum(xw, np.float32(0)).astype(np.float64) - aw.astype(np.float64) * h).astype(np.float32)
+    ref = np.array([0.5 * v * (1 + erf(v / np.sqrt(2))) for v in xw.astype(np.float64)])
+    assert np.abs(g - ref).max() < 8e-7
+    t = torch.nn.functional.gelu(torch.from_numpy(xw)).numpy()
+    assert np.abs(g - ref).max() < np.abs(t - ref).max()   # more accurate than torch's fp32 nn.GELU() (1.3e-6)
+    sel = np.abs(xw) <= 8
+    assert np.sqrt(np.mean((g[sel] - ref[sel]) ** 2)) < 2.5e-7
+
+
 # ----------------------------------------------------------------------------- data-parallel (gloo)
 
 def _dp_worker(rank, world, port, tmp):
