@@ -246,15 +246,16 @@ def rel_l2_vs_oracle(model, sd, batch, steps: int = 4, nsamp: int = 2):
     return out
 
 
-def timed_train_step(p: int, batch_size: int, steps: int = 5, warmup: int = 3, fused_adam: bool = True):
+def timed_train_step(p: int, batch_size: int, steps: int = 5, warmup: int = 3, fused_adam: bool = True,
+                     problem: str = "cavity", act: str = "f32"):
     """fwd -> loss["nmse"].backward() -> Adam.step -> zero_grad (reference src/train_auto.py:233-260) on this GPU,
     fp32 storage, data parallel gradient all-reduce when launched under torchrun.  Secondary number, not the metric.
     fused_adam=False uses the optimizer the reference script builds itself (torch.optim.Adam)."""
     from cfdbench_b200 import FusedAdam
-    model, _ = build_model("f32", p)
+    model, _ = build_model(act, p)
     if torch.distributed.is_initialized():
         model.enable_data_parallel()
-    batch = synth.make_batch(7, batch_size, "cavity")
+    batch = synth.make_batch(7, batch_size, problem)
     tb = {k: torch.from_numpy(v).to(model.device) for k, v in batch.items()}
     opt = (FusedAdam if fused_adam else torch.optim.Adam)(model.parameters(), lr=1e-4)
     ev = []
@@ -272,9 +273,12 @@ def timed_train_step(p: int, batch_size: int, steps: int = 5, warmup: int = 3, f
     ms = float(np.median([a.elapsed_time(z) for a, z in ev]))
     del model
     torch.cuda.empty_cache()
+    world = torch.distributed.get_world_size() if torch.distributed.is_initialized() else 1
     return {"value": 1e3 / ms, "unit": "train steps/s per GPU", "ms_per_step": ms, "batch_per_gpu": batch_size,
-            "what": "fwd + native MseLoss + nmse.backward + " + ("FusedAdam (fno_adam_step)" if fused_adam else
-                                                                   "torch.optim.Adam") + ".step, fp32 storage"}
+            "global_batch": batch_size * world, "problem": problem,
+            "what": "fwd + native MseLoss + nmse.backward" + (" + gradient all-reduce (NCCL AVG, per-segment, overlapped "
+                                                               "with the rest of backward)" if world > 1 else "") +
+                    " + " + ("FusedAdam (fno_adam_step)" if fused_adam else "torch.optim.Adam") + f".step, {act} storage"}
 
 
 def host_cpu():
@@ -509,6 +513,8 @@ def main():
 
     train = timed_train_step(p, min(args.batch, 64))  # all ranks take part (gradient all-reduce under torchrun)
     train["torch_adam_ms_per_step"] = timed_train_step(p, min(args.batch, 64), fused_adam=False)["ms_per_step"]
+    # BASELINE.json configs[2]: cylinder (p = 8), 256 cases per GPU (global 2048 on 8 GPUs), data parallel
+    train_cyl = timed_train_step(synth.n_case_params("cylinder"), args.batch, problem="cylinder")
     if rank != 0:
         if torch.distributed.is_initialized():
             torch.distributed.destroy_process_group()
@@ -572,7 +578,7 @@ def main():
         "gpu_launches": args.steps * head["launches_per_step"],
         "roofline": head["roofline"], "kernels": head["kernels"], "rel_l2": head["rel_l2"],
         ("fp32_storage" if other_act == "f32" else "bf16_storage"): other,
-        "train_step": train,
+        "train_step": train, "train_step_cylinder": train_cyl,
         "clocks": clocks,
     }
     if world == 1 and not args.no_cpu_baseline:

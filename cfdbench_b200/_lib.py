@@ -11,7 +11,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libcfdbench_b200.so")
 
 FNO_MAX_LAYERS = 8
-ABI_VERSION = 2
+ABI_VERSION = 3
 ACT_F32, ACT_BF16 = 0, 1
 EPI_GELU, EPI_GELU_SAVE_PRE, EPI_MUL_DGELU, EPI_PLAIN = 0, 1, 2, 3
 
@@ -65,7 +65,8 @@ class FnoWeightsBwd(C.Structure):
 
 
 class FnoBwdScratch(C.Structure):
-    _fields_ = [("d", C.c_void_p * 2), ("dz1", C.c_void_p), ("gm", C.c_void_p), ("gwk", C.c_void_p)]
+    _fields_ = [("d", C.c_void_p * 2), ("dz1", C.c_void_p), ("gm", C.c_void_p), ("gwk", C.c_void_p),
+                ("partials", C.c_void_p)]
 
 
 BWD_CHUNK = 32
@@ -91,6 +92,7 @@ SIGNATURES = {
     "fno_modes_bytes": (C.c_size_t, [_I]),
     "fno_z_bytes": (C.c_size_t, [_I]),
     "fno_ym_image_bytes": (C.c_size_t, [_I]),
+    "fno_bwd_partials_bytes": (C.c_size_t, []),
     "fno_mode_mix_image": (C.c_int, [_P, _P, _P, _I, _P]),
     "fno_block_fused": (C.c_int, [_P, _P, _P, _P, _P, _I, _P]),
     "fno_pack_spectral_weights": (C.c_int, [_P, _P, _P, _I, _P]),
@@ -121,6 +123,9 @@ SIGNATURES = {
                                 C.c_int64, _P]),
     "fno_forward_train": (C.c_int, [C.POINTER(FnoWeights), _P, _P, _P, _P, C.POINTER(FnoTrainSaved),
                                     C.POINTER(FnoWorkspace), _I, _I, _P]),
+    "fno_backward_ex": (C.c_int, [C.POINTER(FnoWeights), C.POINTER(FnoWeightsBwd), _P, _P, _P, _P,
+                                  C.POINTER(FnoTrainSaved), C.POINTER(FnoGrads), C.POINTER(FnoBwdScratch),
+                                  C.POINTER(FnoWorkspace), _I, _I, _P, C.POINTER(C.c_void_p)]),
     "fno_backward": (C.c_int, [C.POINTER(FnoWeights), C.POINTER(FnoWeightsBwd), _P, _P, _P, _P,
                                C.POINTER(FnoTrainSaved), C.POINTER(FnoGrads), C.POINTER(FnoBwdScratch),
                                C.POINTER(FnoWorkspace), _I, _I, _P]),

@@ -37,13 +37,16 @@ cudaError_t launch_project_tc(const void*, const float*, const float*, const flo
                               float*, int, cudaStream_t);
 template <typename TAct>
 cudaError_t launch_project_bwd(const void*, const float*, const float*, const float*, const float*, const float*,
-                               const float*, float*, float*, float*, float*, float*, int, cudaStream_t);
+                               const float*, float*, float*, float*, int, cudaStream_t);
+int project_bwd_parts(int);
+int project_bwd_row();
+cudaError_t launch_reduce_partials(const float*, int, int, int, float*, cudaStream_t);
 template <typename TP, typename TQ, int NJ, int NI>
-cudaError_t launch_chan_outer(const void*, const void*, float*, float*, int, cudaStream_t);
+cudaError_t launch_chan_outer(const void*, const void*, float*, int*, int, cudaStream_t);
 cudaError_t launch_multistep_metrics(const float*, const float*, const float*, float*, int, int, cudaStream_t);
 cudaError_t launch_spectral_wgrad(const void*, const void*, void*, int, cudaStream_t);
 cudaError_t launch_lift_bwd(const float*, const float*, const float*, const float*, const float*, const float*,
-                            float*, float*, int, int, cudaStream_t);
+                            float*, float*, float*, int, int, cudaStream_t);
 }  // namespace fno
 
 using namespace fno;
@@ -82,6 +85,10 @@ size_t fno_act_bytes(int batch, int act_dtype) {
 size_t fno_modes_bytes(int batch) { return static_cast<size_t>(batch) * kModes * kC * sizeof(float2); }
 size_t fno_z_bytes(int batch) { return static_cast<size_t>(batch) * kH * 2 * kM2 * kC * sizeof(float); }
 size_t fno_ym_image_bytes(int batch) { return ym_image_bytes(batch); }
+size_t fno_bwd_partials_bytes(void) {
+  return (static_cast<size_t>(296) * (kProj * kC + kProj) + static_cast<size_t>(project_bwd_parts(FNO_BWD_CHUNK)) * project_bwd_row() +
+          static_cast<size_t>(16) * kC * (5 + kMaxCaseParams + 1)) * sizeof(float);
+}
 
 int fno_pack_spectral_weights(const void* w1, const void* w2, void* wk, int conj_transpose, void* stream) {
   if (!w1 || !w2 || !wk) return fail(kErrArg, "fno_pack_spectral_weights: null pointer");
@@ -333,14 +340,26 @@ int fno_backward(const fno_weights* w, const fno_weights_bwd* wb, const float* i
                  const float* case_params, const float* dpreds, const fno_train_saved* saved,
                  const fno_grads* g, const fno_bwd_scratch* sc, const fno_workspace* ws, int batch,
                  int act_dtype, void* stream) {
+  return fno_backward_ex(w, wb, inputs, mask, case_params, dpreds, saved, g, sc, ws, batch, act_dtype, stream, nullptr);
+}
+
+int fno_backward_ex(const fno_weights* w, const fno_weights_bwd* wb, const float* inputs, const float* mask,
+                    const float* case_params, const float* dpreds, const fno_train_saved* saved,
+                    const fno_grads* g, const fno_bwd_scratch* sc, const fno_workspace* ws, int batch,
+                    int act_dtype, void* stream, void* const* seg_events) {
   if (!w || !wb || !inputs || !mask || !dpreds || !saved || !g || !sc || !ws || batch <= 0 || bad_dtype(act_dtype))
     return fail(kErrArg, "fno_backward: bad argument");
-  if (!sc->d[0] || !sc->d[1] || !sc->dz1 || !sc->gm || !sc->gwk || !ws->ym || !ws->z)
+  if (!sc->d[0] || !sc->d[1] || !sc->dz1 || !sc->gm || !sc->gwk || !sc->partials || !ws->ym || !ws->z)
     return fail(kErrArg, "fno_backward: null scratch buffer");
   cudaStream_t st = S(stream);
   const int L = w->n_layers, p = w->n_case_params;
   const bool bf = act_dtype == FNO_ACT_BF16;
-  // small gradients are accumulated with atomics: clear them first
+  // Small gradients: every CTA stores its share as one row of sc->partials and a second launch adds the rows up in index
+  // order (reduce_partials_kernel) -- no atomics, so the gradients are bit-for-bit reproducible.  The targets accumulate
+  // over batch chunks / launches: clear them first.
+  float* part_co = sc->partials;                                   // chan_outer: up to 296 rows x (128*32 + 128)
+  float* part_pb = part_co + static_cast<size_t>(296) * (kProj * kC + kProj);   // project_bwd: 16 * chunk rows x 386
+  float* part_lb = part_pb + static_cast<size_t>(project_bwd_parts(FNO_BWD_CHUNK)) * project_bwd_row();   // lift_bwd
   FNO_CUDA(cudaMemsetAsync(g->fc0_w, 0, sizeof(float) * kC * (5 + p), st), "memset");
   FNO_CUDA(cudaMemsetAsync(g->fc0_b, 0, sizeof(float) * kC, st), "memset");
   FNO_CUDA(cudaMemsetAsync(g->fc1_w, 0, sizeof(float) * kProj * kC, st), "memset");
@@ -361,35 +380,49 @@ int fno_backward(const fno_weights* w, const fno_weights_bwd* wb, const float* i
     const float* dp = dpreds + static_cast<size_t>(b0) * 2 * kHW;
     const float* mk = mask + static_cast<size_t>(b0) * kHW;
     cudaError_t e =
-        bf ? launch_project_bwd<__nv_bfloat16>(a_l, dp, mk, pre, w->fc1_w, w->fc1_b, w->fc2_w, dout, sc->dz1, g->fc2_w,
-                                               g->fc2_b, g->fc1_b, nb, st)
-           : launch_project_bwd<float>(a_l, dp, mk, pre, w->fc1_w, w->fc1_b, w->fc2_w, dout, sc->dz1, g->fc2_w,
-                                       g->fc2_b, g->fc1_b, nb, st);
+        bf ? launch_project_bwd<__nv_bfloat16>(a_l, dp, mk, pre, w->fc1_w, w->fc1_b, w->fc2_w, dout, sc->dz1, part_pb, nb, st)
+           : launch_project_bwd<float>(a_l, dp, mk, pre, w->fc1_w, w->fc1_b, w->fc2_w, dout, sc->dz1, part_pb, nb, st);
     FNO_CUDA(e, "project_bwd_kernel");
-    e = bf ? launch_chan_outer<float, __nv_bfloat16, 128, 32>(sc->dz1, a_l, g->fc1_w, nullptr, nb, st)
-           : launch_chan_outer<float, float, 128, 32>(sc->dz1, a_l, g->fc1_w, nullptr, nb, st);
+    const int rows = project_bwd_parts(nb), rs = project_bwd_row();
+    FNO_CUDA(launch_reduce_partials(part_pb, rows, 2 * kProj, rs, g->fc2_w, st), "reduce(fc2.weight)");
+    FNO_CUDA(launch_reduce_partials(part_pb + 2 * kProj, rows, kProj, rs, g->fc1_b, st), "reduce(fc1.bias)");
+    FNO_CUDA(launch_reduce_partials(part_pb + 3 * kProj, rows, 2, rs, g->fc2_b, st), "reduce(fc2.bias)");
+    int n_co = 0;
+    e = bf ? launch_chan_outer<float, __nv_bfloat16, 128, 32>(sc->dz1, a_l, part_co, &n_co, nb, st)
+           : launch_chan_outer<float, float, 128, 32>(sc->dz1, a_l, part_co, &n_co, nb, st);
     FNO_CUDA(e, "chan_outer_kernel(fc1)");
+    FNO_CUDA(launch_reduce_partials(part_co, n_co, kProj * kC, kProj * kC + kProj, g->fc1_w, st), "reduce(fc1.weight)");
   }
+  auto mark = [&](int seg) -> cudaError_t {   // the gradients of segment `seg` are final from here on (stream order)
+    if (seg_events == nullptr || seg_events[seg] == nullptr) return cudaSuccess;
+    return cudaEventRecord(static_cast<cudaEvent_t>(seg_events[seg]), st);
+  };
+  FNO_CUDA(mark(0), "cudaEventRecord(fc1/fc2 gradients)");
   // ---- Fourier blocks, last to first
   const float inv = 1.f / static_cast<float>(kHW);
   int cur = 0;
   for (int l = L - 1; l >= 0; --l) {
     float* dpre = sc->d[cur];
     float* dnext = sc->d[cur ^ 1];
-    cudaError_t e = bf ? launch_chan_outer<float, __nv_bfloat16, 32, 32>(dpre, saved->act[l], g->w0_w[l], g->w0_b[l], batch, st)
-                       : launch_chan_outer<float, float, 32, 32>(dpre, saved->act[l], g->w0_w[l], g->w0_b[l], batch, st);
+    int n_co = 0;
+    cudaError_t e = bf ? launch_chan_outer<float, __nv_bfloat16, 32, 32>(dpre, saved->act[l], part_co, &n_co, batch, st)
+                       : launch_chan_outer<float, float, 32, 32>(dpre, saved->act[l], part_co, &n_co, batch, st);
     FNO_CUDA(e, "chan_outer_kernel(w0)");
+    FNO_CUDA(launch_reduce_partials(part_co, n_co, kC * kC, kC * kC + kC, g->w0_w[l], st), "reduce(w0.weight)");
+    FNO_CUDA(launch_reduce_partials(part_co + kC * kC, n_co, kC, kC * kC + kC, g->w0_b[l], st), "reduce(w0.bias)");
     FNO_TRY(fno_spectral_dft_fwd(dpre, sc->gm, batch, FNO_ACT_F32, inv, 2.f * inv, stream));
     FNO_CUDA(launch_spectral_wgrad(saved->xm[l], sc->gm, sc->gwk, batch, st), "spectral_wgrad_kernel");
     FNO_TRY(fno_unpack_spectral_grads(sc->gwk, g->spec_w1[l], g->spec_w2[l], stream));
+    FNO_CUDA(mark(1 + (L - 1 - l)), "cudaEventRecord(block gradients)");
     FNO_TRY(fno_mode_mix(sc->gm, wb->spec_wkT[l], ws->ym, batch, stream));
     FNO_TRY(fno_spectral_inv_kx(ws->ym, ws->z, batch, 1.f, 1.f, stream));
     FNO_TRY(fno_block_out(l > 0 ? FNO_EPI_MUL_DGELU : FNO_EPI_PLAIN, ws->z, dpre, wb->w0[l], nullptr, dnext, nullptr,
                           l > 0 ? saved->pre[l - 1] : nullptr, batch, FNO_ACT_F32, stream));
     cur ^= 1;
   }
-  FNO_CUDA(launch_lift_bwd(sc->d[cur], inputs, mask, case_params, w->gx, w->gy, g->fc0_w, g->fc0_b, batch, p, st),
+  FNO_CUDA(launch_lift_bwd(sc->d[cur], inputs, mask, case_params, w->gx, w->gy, g->fc0_w, g->fc0_b, part_lb, batch, p, st),
            "lift_bwd_kernel");
+  FNO_CUDA(mark(L + 1), "cudaEventRecord(fc0 gradients)");
   return kOk;
 }
 

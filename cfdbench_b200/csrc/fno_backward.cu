@@ -32,6 +32,44 @@ __device__ __forceinline__ void gelu_both(float x, float& g, float& dg) {
 // ------------------------------------------------------------------------------------ project bwd
 constexpr int kPbThreads = 128;
 constexpr int kPbPix = 256;
+constexpr int kPbOut = 3 * kProj + 2;   // per-CTA partial row: g_w2 (2 x 128) | g_b1 (128) | g_b2 (2)
+
+// out[i] += sum over parts (in index order) of partial[part][i]: the second, deterministic half of every small-gradient
+// reduction (the first half = one plain store per CTA).  Replaces float atomics, whose summation order -- and therefore the
+// last bits of every gradient and the whole training trajectory -- changed from run to run.
+__global__ void __launch_bounds__(256) reduce_partials_kernel(const float* __restrict__ partial, int n_parts, int n_out,
+                                                              int row_stride, float* __restrict__ out) {
+  // block = 32 columns x 8 row groups: thread (tx, ty) adds rows ty, ty+8, .. (four independent loads in flight), the
+  // eight group sums are then added in index order -> a fixed summation tree, independent of scheduling
+  __shared__ float red[8][33];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int i = blockIdx.x * 32 + tx;
+  float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+  if (i < n_out) {
+    int c = ty;
+    for (; c + 24 < n_parts; c += 32) {
+      s0 += partial[static_cast<size_t>(c) * row_stride + i];
+      s1 += partial[static_cast<size_t>(c + 8) * row_stride + i];
+      s2 += partial[static_cast<size_t>(c + 16) * row_stride + i];
+      s3 += partial[static_cast<size_t>(c + 24) * row_stride + i];
+    }
+    for (; c < n_parts; c += 8) s0 += partial[static_cast<size_t>(c) * row_stride + i];
+  }
+  red[ty][tx] = (s0 + s1) + (s2 + s3);
+  __syncthreads();
+  if (ty == 0 && i < n_out) {
+    float s = red[0][tx];
+#pragma unroll
+    for (int r = 1; r < 8; ++r) s += red[r][tx];
+    out[i] += s;
+  }
+}
+cudaError_t launch_reduce_partials(const float* partial, int n_parts, int n_out, int row_stride, float* out,
+                                   cudaStream_t stream) {
+  if (n_parts <= 0 || n_out <= 0) return cudaSuccess;
+  reduce_partials_kernel<<<(n_out + 31) / 32, 256, 0, stream>>>(partial, n_parts, n_out, row_stride, out);
+  return cudaGetLastError();
+}
 
 template <typename TAct>
 struct PbSmem {
@@ -39,8 +77,8 @@ struct PbSmem {
   alignas(16) float w1[kProj][kC];
   alignas(16) float b1[kProj];
   alignas(16) float w2[2][kProj];
-  alignas(16) float acc_w2[2][kProj];
-  alignas(16) float acc_b1[kProj];
+  alignas(16) float acc[kPbThreads / 32][3][kProj];   // per-warp partials of (g_w2[0][j], g_w2[1][j], g_b1[j]): fixed order
+  alignas(16) float acc_b2[kPbThreads / 32][2];
   alignas(8) uint64_t bar;
 };
 
@@ -53,7 +91,7 @@ __global__ void __launch_bounds__(kPbThreads)
                        const float* __restrict__ w1, const float* __restrict__ b1, const float* __restrict__ w2,
                        float* __restrict__ d_out,         // [B][32][4096]: dpre_{L-1} (pre != null) or d a_L
                        float* __restrict__ dz1,           // [B][128][4096]
-                       float* __restrict__ g_w2, float* __restrict__ g_b2, float* __restrict__ g_b1) {
+                       float* __restrict__ partial) {   // [CTA][kPbOut]: (g_w2 256 | g_b1 128 | g_b2 2), reduced in CTA order
   extern __shared__ __align__(128) unsigned char smem_raw[];
   PbSmem<TAct>& sm = *reinterpret_cast<PbSmem<TAct>*>(smem_raw);
   const int tid = threadIdx.x, lane = tid & 31;
@@ -76,9 +114,6 @@ __global__ void __launch_bounds__(kPbThreads)
     sm.b1[j] = b1[j];
     sm.w2[0][j] = w2[j];
     sm.w2[1][j] = w2[kProj + j];
-    sm.acc_w2[0][j] = 0.f;
-    sm.acc_w2[1][j] = 0.f;
-    sm.acc_b1[j] = 0.f;
   }
   __syncthreads();
   mbar_wait(&sm.bar, 0);
@@ -130,18 +165,18 @@ __global__ void __launch_bounds__(kPbThreads)
     const float p0 = warp_sum(d0.x * gx_ + d0.y * gy_);
     const float p1 = warp_sum(d1.x * gx_ + d1.y * gy_);
     const float pb = warp_sum(dz.x + dz.y);
-    if (lane == 0) {
-      atomicAdd(&sm.acc_w2[0][j], p0);
-      atomicAdd(&sm.acc_w2[1][j], p1);
-      atomicAdd(&sm.acc_b1[j], pb);
+    if (lane == 0) {   // no atomics anywhere in the gradient path: every slot has one writer, every sum a fixed order
+      sm.acc[tid >> 5][0][j] = p0;
+      sm.acc[tid >> 5][1][j] = p1;
+      sm.acc[tid >> 5][2][j] = pb;
     }
   }
   // fc2 bias gradient
   {
     const float s0 = warp_sum(d0.x + d0.y), s1 = warp_sum(d1.x + d1.y);
     if (lane == 0) {
-      atomicAdd(g_b2 + 0, s0);
-      atomicAdd(g_b2 + 1, s1);
+      sm.acc_b2[tid >> 5][0] = s0;
+      sm.acc_b2[tid >> 5][1] = s1;
     }
   }
   // d a_L (optionally times GELU'(pre_{L-1}))
@@ -157,17 +192,27 @@ __global__ void __launch_bounds__(kPbThreads)
     *reinterpret_cast<float2*>(d_out + base + static_cast<size_t>(i) * kHW) = v;
   }
   __syncthreads();
+  float* prow = partial + (static_cast<size_t>(blockIdx.y) * gridDim.x + blockIdx.x) * kPbOut;
   for (int j = tid; j < kProj; j += kPbThreads) {
-    atomicAdd(g_w2 + j, sm.acc_w2[0][j]);
-    atomicAdd(g_w2 + kProj + j, sm.acc_w2[1][j]);
-    atomicAdd(g_b1 + j, sm.acc_b1[j]);
+    float t0 = 0.f, t1 = 0.f, t2 = 0.f;
+#pragma unroll
+    for (int w = 0; w < kPbThreads / 32; ++w) { t0 += sm.acc[w][0][j]; t1 += sm.acc[w][1][j]; t2 += sm.acc[w][2][j]; }
+    prow[j] = t0;
+    prow[kProj + j] = t1;
+    prow[2 * kProj + j] = t2;
+  }
+  if (tid < 2) {
+    float t = 0.f;
+#pragma unroll
+    for (int w = 0; w < kPbThreads / 32; ++w) t += sm.acc_b2[w][tid];
+    prow[3 * kProj + tid] = t;
   }
 }
 
 template <typename TAct>
 cudaError_t launch_project_bwd(const void* a, const float* dpreds, const float* mask, const float* pre,
                                const float* w1, const float* b1, const float* w2, float* d_out, float* dz1,
-                               float* g_w2, float* g_b2, float* g_b1, int batch, cudaStream_t stream) {
+                               float* partial, int batch, cudaStream_t stream) {
   auto kern = project_bwd_kernel<TAct>;
   constexpr size_t smem = sizeof(PbSmem<TAct>);
   static bool configured = false;
@@ -178,15 +223,17 @@ cudaError_t launch_project_bwd(const void* a, const float* dpreds, const float* 
   }
   dim3 grid(kHW / kPbPix, batch);
   kern<<<grid, kPbThreads, smem, stream>>>(static_cast<const TAct*>(a), dpreds, mask, pre, w1, b1, w2, d_out, dz1,
-                                           g_w2, g_b2, g_b1);
+                                           partial);
   return cudaGetLastError();
 }
+int project_bwd_parts(int batch) { return (kHW / kPbPix) * batch; }   // partial rows written by one launch
+int project_bwd_row() { return kPbOut; }
 template cudaError_t launch_project_bwd<float>(const void*, const float*, const float*, const float*, const float*,
-                                               const float*, const float*, float*, float*, float*, float*, float*,
+                                               const float*, const float*, float*, float*, float*,
                                                int, cudaStream_t);
 template cudaError_t launch_project_bwd<__nv_bfloat16>(const void*, const float*, const float*, const float*,
                                                        const float*, const float*, const float*, float*, float*,
-                                                       float*, float*, float*, int, cudaStream_t);
+                                                       float*, int, cudaStream_t);
 
 // ------------------------------------------------------------------------------------- chan outer
 // out[j][i] += sum_{b,pix} P[b][j][pix] * Q[b][i][pix];   rowsum[j] += sum_{b,pix} P[b][j][pix]
@@ -209,8 +256,8 @@ __device__ __forceinline__ float4 load4<__nv_bfloat16>(const __nv_bfloat16* p) {
 
 template <typename TP, typename TQ, int NJ, int NI>
 __global__ void __launch_bounds__(kCoThreads)
-    chan_outer_kernel(const TP* __restrict__ P, const TQ* __restrict__ Q, float* __restrict__ out,
-                      float* __restrict__ rowsum, int batch) {
+    chan_outer_kernel(const TP* __restrict__ P, const TQ* __restrict__ Q, float* __restrict__ partial, int batch) {
+  // partial[CTA][NJ*NI + NJ]: this CTA's share of G[j][i] and of the row sums sum_pix P[j][pix] (the bias gradient)
   constexpr int TJ = (NJ * NI / kCoThreads >= 16) ? 4 : 2;
   constexpr int TI = NJ * NI / kCoThreads / TJ;
   constexpr int NTI = NI / TI;
@@ -260,16 +307,18 @@ __global__ void __launch_bounds__(kCoThreads)
       }
     }
   }
+  float* prow = partial + static_cast<size_t>(blockIdx.x) * (NJ * NI + NJ);
 #pragma unroll
   for (int a = 0; a < TJ; ++a) {
 #pragma unroll
-    for (int c = 0; c < TI; ++c) atomicAdd(out + (tj * TJ + a) * NI + ti * TI + c, acc[a][c]);
-    if (rowsum != nullptr && ti == 0) atomicAdd(rowsum + tj * TJ + a, rs[a]);
+    for (int c = 0; c < TI; ++c) prow[(tj * TJ + a) * NI + ti * TI + c] = acc[a][c];
+    if (ti == 0) prow[NJ * NI + tj * TJ + a] = rs[a];
   }
 }
 
+// returns the number of partial rows written (= grid size) through *n_parts
 template <typename TP, typename TQ, int NJ, int NI>
-cudaError_t launch_chan_outer(const void* P, const void* Q, float* out, float* rowsum, int batch, cudaStream_t stream) {
+cudaError_t launch_chan_outer(const void* P, const void* Q, float* partial, int* n_parts, int batch, cudaStream_t stream) {
   auto kern = chan_outer_kernel<TP, TQ, NJ, NI>;
   constexpr size_t smem = static_cast<size_t>(NJ + NI) * kCoPitch * sizeof(float);
   static bool configured = false;
@@ -280,13 +329,14 @@ cudaError_t launch_chan_outer(const void* P, const void* Q, float* out, float* r
   }
   const int items = batch * (kHW / kCoPix);
   const int grid = items < 296 ? items : 296;
-  kern<<<grid, kCoThreads, smem, stream>>>(static_cast<const TP*>(P), static_cast<const TQ*>(Q), out, rowsum, batch);
+  kern<<<grid, kCoThreads, smem, stream>>>(static_cast<const TP*>(P), static_cast<const TQ*>(Q), partial, batch);
+  *n_parts = grid;
   return cudaGetLastError();
 }
-template cudaError_t launch_chan_outer<float, float, 128, 32>(const void*, const void*, float*, float*, int, cudaStream_t);
-template cudaError_t launch_chan_outer<float, __nv_bfloat16, 128, 32>(const void*, const void*, float*, float*, int, cudaStream_t);
-template cudaError_t launch_chan_outer<float, float, 32, 32>(const void*, const void*, float*, float*, int, cudaStream_t);
-template cudaError_t launch_chan_outer<float, __nv_bfloat16, 32, 32>(const void*, const void*, float*, float*, int, cudaStream_t);
+template cudaError_t launch_chan_outer<float, float, 128, 32>(const void*, const void*, float*, int*, int, cudaStream_t);
+template cudaError_t launch_chan_outer<float, __nv_bfloat16, 128, 32>(const void*, const void*, float*, int*, int, cudaStream_t);
+template cudaError_t launch_chan_outer<float, float, 32, 32>(const void*, const void*, float*, int*, int, cudaStream_t);
+template cudaError_t launch_chan_outer<float, __nv_bfloat16, 32, 32>(const void*, const void*, float*, int*, int, cudaStream_t);
 
 // --------------------------------------------------------------------------------- spectral wgrad
 // gWk[k][i][o] = sum_b conj(X[k][b][i]) * G[k][b][o];  one CTA per mode k, lane = o, warps split the batch.
@@ -348,8 +398,8 @@ __global__ void __launch_bounds__(kLbThreads)
                     const float* __restrict__ inputs,  // [B][2][4096]
                     const float* __restrict__ mask,    // [B][4096]
                     const float* __restrict__ params,  // [B][p]
-                    const float* __restrict__ gx, const float* __restrict__ gy, float* __restrict__ g_w,
-                    float* __restrict__ g_b, int batch, int p) {
+                    const float* __restrict__ gx, const float* __restrict__ gy, float* __restrict__ partial,
+                    int batch, int p) {   // partial[blockIdx.y][c][nin + 1]: weight row of channel c, then its bias
   __shared__ float red[kLbThreads / 32][6];
   __shared__ float tot[6];
   const int c = blockIdx.x;
@@ -399,19 +449,36 @@ __global__ void __launch_bounds__(kLbThreads)
     __syncthreads();
   }
   if (tid == 0) {
+    float* prow = partial + (static_cast<size_t>(blockIdx.y) * kC + c) * (nin + 1);
 #pragma unroll
-    for (int q = 0; q < 5; ++q) atomicAdd(g_w + c * nin + q, gw_acc[q]);
-    for (int q = 0; q < p; ++q) atomicAdd(g_w + c * nin + 5 + q, gp_acc[q]);
-    atomicAdd(g_b + c, gb_acc);
+    for (int q = 0; q < 5; ++q) prow[q] = gw_acc[q];
+    for (int q = 0; q < p; ++q) prow[5 + q] = gp_acc[q];
+    prow[nin] = gb_acc;
   }
 }
 
+// g_w[c][q] += sum_y partial[y][c][q], g_b[c] += sum_y partial[y][c][nin]   (fixed order)
+__global__ void lift_bwd_reduce_kernel(const float* __restrict__ partial, int n_parts, int nin, float* __restrict__ g_w,
+                                       float* __restrict__ g_b) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= kC * (nin + 1)) return;
+  const int c = i / (nin + 1), q = i % (nin + 1);
+  float s = 0.f;
+  for (int y = 0; y < n_parts; ++y) s += partial[(static_cast<size_t>(y) * kC + c) * (nin + 1) + q];
+  if (q < nin) g_w[c * nin + q] += s;
+  else g_b[c] += s;
+}
+
 cudaError_t launch_lift_bwd(const float* da0, const float* inputs, const float* mask, const float* params,
-                            const float* gx, const float* gy, float* g_w, float* g_b, int batch, int p,
+                            const float* gx, const float* gy, float* g_w, float* g_b, float* partial, int batch, int p,
                             cudaStream_t stream) {
   if (p < 0 || p > kMaxCaseParams) return cudaErrorInvalidValue;
   dim3 grid(kC, batch < 16 ? batch : 16);
-  lift_bwd_kernel<<<grid, kLbThreads, 0, stream>>>(da0, inputs, mask, params, gx, gy, g_w, g_b, batch, p);
+  lift_bwd_kernel<<<grid, kLbThreads, 0, stream>>>(da0, inputs, mask, params, gx, gy, partial, batch, p);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return e;
+  const int n = kC * (5 + p + 1);
+  lift_bwd_reduce_kernel<<<(n + 127) / 128, 128, 0, stream>>>(partial, static_cast<int>(grid.y), 5 + p, g_w, g_b);
   return cudaGetLastError();
 }
 

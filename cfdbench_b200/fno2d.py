@@ -16,6 +16,7 @@ Extras that the reference does not have (all optional, defaults keep reference b
 from __future__ import annotations
 
 import ctypes as C
+import os
 from typing import Dict, List, Optional
 
 import numpy as np
@@ -153,6 +154,11 @@ class Fno2d(AutoCfdModel):
         self._ws_cache: dict = {}
         self._dp_group = None
         self._dp_enabled = False
+        self._dp_events = None
+        self._dp_stream = None
+        # how the flat gradient buffer is all-reduced: "one" collective after backward, "two" (upper half of the network
+        # while the lower half is still in backward) or "all" (one per gradient group); measured in profiles/README.md
+        self.dp_segments = os.environ.get("FNO_DP_SEGMENTS", "one")
         # CUDA-graph replay of device-resident rollouts: one capture per (batch, steps), the 18 launches of every
         # step replayed as one graph (B=256: 591 -> 544 us/step, B=1: 2.09 -> 1.48 ms per 20 steps).  False = launch
         # every kernel on the stream.
@@ -372,13 +378,60 @@ class Fno2d(AutoCfdModel):
         sc = _lib.FnoBwdScratch()
         sc.d[0], sc.d[1] = d0.data_ptr(), d1.data_ptr()
         sc.dz1, sc.gm, sc.gwk = dz1.data_ptr(), gm.data_ptr(), gwk.data_ptr()
-        _lib.check(lib.fno_backward(C.byref(pk["struct"]), C.byref(pk["struct_bwd"]), inputs.data_ptr(),
-                                    mask4.data_ptr(), case_params.data_ptr(), dpreds.data_ptr(), C.byref(sv),
-                                    C.byref(g), C.byref(sc), C.byref(ws), b, self._act_code(), self._stream()),
-                   "fno_backward")
-        if self._dp_enabled:
-            from .dp import allreduce_mean_
-            allreduce_mean_(flat, self._dp_group)
+        partials = torch.empty(lib.fno_bwd_partials_bytes(), dtype=torch.uint8, device=dev)
+        sc.partials = partials.data_ptr()
+        if not self._dp_enabled or self.dp_segments == "one":
+            _lib.check(lib.fno_backward(C.byref(pk["struct"]), C.byref(pk["struct_bwd"]), inputs.data_ptr(),
+                                        mask4.data_ptr(), case_params.data_ptr(), dpreds.data_ptr(), C.byref(sv),
+                                        C.byref(g), C.byref(sc), C.byref(ws), b, self._act_code(), self._stream()),
+                       "fno_backward")
+            if self._dp_enabled:   # one all-reduce (NCCL: ReduceOp.AVG, no division kernel) of the whole flat buffer
+                from .dp import allreduce_mean_
+                allreduce_mean_(flat, self._dp_group)
+            return [views[name] for name, _ in self.named_parameters()]
+        # Optional: reduce the flat buffer segment by segment, each as soon as its gradients are final -- the native
+        # backward records one event per segment (fc1/fc2, block L-1 .. block 0, fc0) and a side stream starts the NCCL
+        # all-reduce (ReduceOp.AVG) of that slice while the remaining backward kernels still run on the main stream.
+        # Measured on 2 x B200 (tools/time_train_dp.py): no gain -- cylinder B=256/GPU 4.89 ms in every mode (4.83 ms on one
+        # GPU), cavity B=64/GPU 1.83 ("one") / 1.87 ("two") / 2.04 ms ("all"): the 9.5 MB collective costs less than the
+        # extra launches and the SM contention between NCCL's kernels and the persistent backward kernels.
+        from .dp import allreduce_mean_async
+        ends = {name: off + n for name, _p, off, n in layout}
+        starts = {name: off for name, _p, off, n in layout}
+        # (event index, begin, end): event k of fno_backward_ex = fc1/fc2 (0), block L-1 .. block 0 (1..L), fc0 (L+1)
+        mode = self.dp_segments
+        if mode == "all":      # one collective per gradient group, each as early as possible
+            segs = [(0, starts["fc1.weight"], ends["fc2.bias"])]
+            for l in range(L - 1, -1, -1):
+                segs.append((L - l, starts[f"blocks.{l}.conv0.weights1"], ends[f"blocks.{l}.w0.bias"]))
+            segs.append((L + 1, starts["fc0.weight"], ends["fc0.bias"]))
+        elif mode == "two":    # upper half of the network (contiguous tail of the buffer) early, the rest at the end
+            mid = L // 2
+            cut = starts[f"blocks.{mid}.conv0.weights1"]
+            segs = [(L - mid, cut, total), (L + 1, 0, cut)]
+        else:                  # "one": a single all-reduce of the whole buffer after the backward pass
+            segs = [(L + 1, 0, total)]
+        assert sum(e - s_ for _, s_, e in segs) == total   # the segments tile the buffer
+        if self._dp_events is None or len(self._dp_events) != L + 2:
+            self._dp_events = [torch.cuda.Event() for _ in range(L + 2)]
+            self._dp_stream = torch.cuda.Stream(device=dev)
+            for ev in self._dp_events:
+                ev.record()   # creates the underlying cudaEvent_t
+        handles = (C.c_void_p * (L + 2))(*[ev.cuda_event for ev in self._dp_events])
+        main = torch.cuda.current_stream(dev)
+        _lib.check(lib.fno_backward_ex(C.byref(pk["struct"]), C.byref(pk["struct_bwd"]), inputs.data_ptr(),
+                                       mask4.data_ptr(), case_params.data_ptr(), dpreds.data_ptr(), C.byref(sv),
+                                       C.byref(g), C.byref(sc), C.byref(ws), b, self._act_code(), self._stream(), handles),
+                   "fno_backward_ex")
+        works = []
+        flat.record_stream(self._dp_stream)
+        with torch.cuda.stream(self._dp_stream):
+            for k, s_, e in segs:
+                self._dp_stream.wait_event(self._dp_events[k])
+                works.append(allreduce_mean_async(flat[s_:e], self._dp_group))
+        for wk in works:
+            wk.wait()   # the main stream waits for the collectives
+        main.wait_stream(self._dp_stream)
         return [views[name] for name, _ in self.named_parameters()]
 
     # -------------------------------------------------------------------------------- public API

@@ -34,7 +34,7 @@
 extern "C" {
 #endif
 
-#define FNO_ABI_VERSION 2
+#define FNO_ABI_VERSION 3
 #define FNO_MAX_LAYERS 8
 
 enum { FNO_ACT_F32 = 0, FNO_ACT_BF16 = 1 };
@@ -75,6 +75,7 @@ size_t fno_act_bytes(int batch, int act_dtype);
 size_t fno_modes_bytes(int batch);
 size_t fno_z_bytes(int batch);
 size_t fno_ym_image_bytes(int batch);
+size_t fno_bwd_partials_bytes(void);
 
 /* weights1, weights2: (32,32,12,12) complex64 as stored by the reference (fno2d.py:31-51).
  * conj_transpose=0 -> wk[k][i][o] = W[i][o][k] (forward); 1 -> wk[k][o][i] = conj(W[i][o][k]) (adjoint). */
@@ -188,6 +189,8 @@ typedef struct fno_bwd_scratch {
   float* dz1;    /* float32 [min(B,FNO_BWD_CHUNK)][128][64][64] */
   void* gm;      /* complex64 [B][288][32]: scaled modes of the block's upstream gradient */
   void* gwk;     /* complex64 [288][32][32] */
+  float* partials; /* fno_bwd_partials_bytes() bytes: per-CTA shares of the small gradients (fc0/fc1/fc2/w0), summed in a
+                    * fixed order by a second launch instead of float atomics -> bit-reproducible gradients */
 } fno_bwd_scratch;
 #define FNO_BWD_CHUNK 32
 
@@ -201,6 +204,14 @@ int fno_backward(const fno_weights* w, const fno_weights_bwd* wb, const float* i
                  const float* case_params, const float* dpreds, const fno_train_saved* saved,
                  const fno_grads* grads, const fno_bwd_scratch* scratch, const fno_workspace* ws, int batch,
                  int act_dtype, void* stream);
+/* Same, recording CUDA events as gradient segments become final so that the caller can start their all-reduce while
+ * the rest of the backward pass still runs (data-parallel training): seg_events[0] after the fc1 / fc2
+ * gradients, seg_events[1 + i] after the gradients of block (n_layers - 1 - i), seg_events[n_layers + 1] after the fc0
+ * gradients.  seg_events = NULL or a NULL entry: nothing recorded there.  Entries are cudaEvent_t. */
+int fno_backward_ex(const fno_weights* w, const fno_weights_bwd* wb, const float* inputs, const float* mask,
+                 const float* case_params, const float* dpreds, const fno_train_saved* saved,
+                 const fno_grads* grads, const fno_bwd_scratch* scratch, const fno_workspace* ws, int batch,
+                 int act_dtype, void* stream, void* const* seg_events);
 
 /* Rollout evaluation on the device (reference src/test_multistep.py:73-83,153-177 get_metrics on the
  * masked u channel, three .item() syncs per step and case there).  preds_seq [S][B][2][64][64], label_u and mask

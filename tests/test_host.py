@@ -34,7 +34,7 @@ def test_library_exports_every_declared_symbol(built_lib):
         assert hasattr(lib, name), f"{name} is declared in include/cfdbench_b200.h but not exported"
     from cfdbench_b200 import _lib
     assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
-    assert _lib.load().fno_version() == _lib.ABI_VERSION == 2
+    assert _lib.load().fno_version() == _lib.ABI_VERSION == 3
 
 
 def test_struct_layouts_match_header():
@@ -44,7 +44,7 @@ def test_struct_layouts_match_header():
     assert ctypes.sizeof(_lib.FnoWorkspace) == 6 * P
     assert ctypes.sizeof(_lib.FnoTrainSaved) == P * (9 + 8 + 8)
     assert ctypes.sizeof(_lib.FnoGrads) == P * (2 + 4 * 8 + 4)
-    assert ctypes.sizeof(_lib.FnoBwdScratch) == 5 * P
+    assert ctypes.sizeof(_lib.FnoBwdScratch) == 6 * P
     assert ctypes.sizeof(_lib.FnoWeightsBwd) == 16 * P
     assert ctypes.sizeof(_lib.FnoAdamTensors) == 8 + 32 * (4 * P + 8)
 
