@@ -88,6 +88,7 @@ _F = C.c_float
 SIGNATURES = {
     "fno_version": (C.c_int, []),
     "fno_last_error": (C.c_char_p, []),
+    "fno_destroy": (C.c_int, []),
     "fno_act_bytes": (C.c_size_t, [_I, _I]),
     "fno_modes_bytes": (C.c_size_t, [_I]),
     "fno_z_bytes": (C.c_size_t, [_I]),

@@ -51,6 +51,13 @@ cudaError_t launch_lift_bwd(const float*, const float*, const float*, const floa
 
 using namespace fno;
 
+namespace fno {
+void block_tc_release(int);
+void block_fused_release(int);
+void dft_fwd_tc_release(int);
+}  // namespace fno
+static cudaEvent_t g_chunk_events[64][2][16] = {};   // fno_rollout_host_chunked: [device][upload|compute][chunk]
+
 static thread_local char g_err[512] = "";
 
 static int fail(int code, const char* what, cudaError_t e = cudaSuccess) {
@@ -77,6 +84,23 @@ static inline bool bad_dtype(int d) { return d != FNO_ACT_F32 && d != FNO_ACT_BF
 extern "C" {
 
 int fno_version(void) { return FNO_ABI_VERSION; }
+
+int fno_destroy(void) {
+  int dev = 0;
+  FNO_CUDA(cudaGetDevice(&dev), "cudaGetDevice");
+  if (dev < 0 || dev >= 64) return fail(kErrArg, "fno_destroy: device index");
+  FNO_CUDA(cudaDeviceSynchronize(), "cudaDeviceSynchronize");
+  block_tc_release(dev);
+  block_fused_release(dev);
+  dft_fwd_tc_release(dev);
+  for (int k = 0; k < 2; ++k)
+    for (int c = 0; c < 16; ++c)
+      if (g_chunk_events[dev][k][c]) {
+        cudaEventDestroy(g_chunk_events[dev][k][c]);
+        g_chunk_events[dev][k][c] = nullptr;
+      }
+  return kOk;
+}
 const char* fno_last_error(void) { return g_err; }
 
 size_t fno_act_bytes(int batch, int act_dtype) {
@@ -278,7 +302,7 @@ int fno_rollout_host_chunked(const fno_weights* w, const float* inputs_host, con
   if (!w || !inputs_host || !mask_host || !preds_host || !ws_chunks || !dev_io_chunks || batch <= 0 || n_chunks <= 0 ||
       n_chunks > kMaxChunks || batch % n_chunks != 0)
     return fail(kErrArg, "fno_rollout_host_chunked: bad argument");
-  static cudaEvent_t ev[64][2][kMaxChunks] = {};
+  auto& ev = g_chunk_events;
   int dev = 0;
   FNO_CUDA(cudaGetDevice(&dev), "cudaGetDevice");
   if (dev < 0 || dev >= 64) return fail(kErrArg, "fno_rollout_host_chunked: device index");

@@ -215,12 +215,9 @@ cudaError_t launch_project_bwd(const void* a, const float* dpreds, const float* 
                                float* partial, int batch, cudaStream_t stream) {
   auto kern = project_bwd_kernel<TAct>;
   constexpr size_t smem = sizeof(PbSmem<TAct>);
-  static bool configured = false;
-  if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    configured = true;
-  }
+  static PerDeviceLaunch pd;
+  cudaError_t e0 = per_device_setup(kern, smem, pd);
+  if (e0 != cudaSuccess) return e0;
   dim3 grid(kHW / kPbPix, batch);
   kern<<<grid, kPbThreads, smem, stream>>>(static_cast<const TAct*>(a), dpreds, mask, pre, w1, b1, w2, d_out, dz1,
                                            partial);
@@ -321,12 +318,9 @@ template <typename TP, typename TQ, int NJ, int NI>
 cudaError_t launch_chan_outer(const void* P, const void* Q, float* partial, int* n_parts, int batch, cudaStream_t stream) {
   auto kern = chan_outer_kernel<TP, TQ, NJ, NI>;
   constexpr size_t smem = static_cast<size_t>(NJ + NI) * kCoPitch * sizeof(float);
-  static bool configured = false;
-  if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    configured = true;
-  }
+  static PerDeviceLaunch pd;
+  cudaError_t e0 = per_device_setup(kern, smem, pd);
+  if (e0 != cudaSuccess) return e0;
   const int items = batch * (kHW / kCoPix);
   const int grid = items < 296 ? items : 296;
   kern<<<grid, kCoThreads, smem, stream>>>(static_cast<const TP*>(P), static_cast<const TQ*>(Q), partial, batch);

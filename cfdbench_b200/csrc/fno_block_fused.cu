@@ -497,6 +497,14 @@ extern "C" int fno_debug_fused_trace(void* p) {
 }
 #endif
 
+void block_fused_release(int dev) {
+  if (dev < 0 || dev >= 64) return;
+  FzTables& t = g_fz[dev];
+  if (t.etab) cudaFree(t.etab);
+  if (t.ftab) cudaFree(t.ftab);
+  t = FzTables();
+}
+
 size_t ym_image_bytes(int batch) { return static_cast<size_t>(batch) * kYmImgBytes; }
 
 cudaError_t launch_block_fused(const void* ym_img, const void* x, const float* w0t, const float* bias, void* out, int batch,

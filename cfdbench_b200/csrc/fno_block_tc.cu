@@ -389,24 +389,24 @@ static cudaError_t ensure_etab(const float** out, cudaStream_t stream) {
   return cudaSuccess;
 }
 
+void block_tc_release(int dev) {
+  if (dev >= 0 && dev < 64 && g_etab[dev] != nullptr) {
+    cudaFree(g_etab[dev]);
+    g_etab[dev] = nullptr;
+  }
+}
+
 template <typename TAct, int EPI>
 static cudaError_t launch_one(const void* z, const void* x, const float* w0t, const float* bias, void* out,
                               float* pre_out, const float* pre_in, int batch, cudaStream_t stream) {
   auto kern = block_tc_kernel<TAct, EPI>;
   constexpr size_t smem = sizeof(BtSmem);
-  static bool configured = false;
-  static int n_sm = 0;
-  if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    int dev = 0;
-    cudaGetDevice(&dev);
-    e = cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
-    if (e != cudaSuccess) return e;
-    configured = true;
-  }
+  static PerDeviceLaunch pd;
+  int n_sm = 0;
+  cudaError_t e = per_device_setup(kern, smem, pd, &n_sm);
+  if (e != cudaSuccess) return e;
   const float* etab = nullptr;
-  cudaError_t e = ensure_etab(&etab, stream);
+  e = ensure_etab(&etab, stream);
   if (e != cudaSuccess) return e;
   const int n_tiles = batch * kBtTilesPerSample;
   const int grid = n_tiles < 2 * n_sm ? (n_tiles + 1) / 2 : n_sm;

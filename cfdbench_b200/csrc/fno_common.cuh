@@ -105,6 +105,33 @@ inline cudaError_t launch_chained(void (*kern)(KArgs...), dim3 grid, dim3 block,
 }
 
 // ------------------------------------------------------------------------------------------------
+// Per-DEVICE launcher state (one process may drive several GPUs): the opt-in dynamic shared-memory size is a per-device
+// function attribute and the SM count differs per device, so both are cached per device index, not per process.
+// ------------------------------------------------------------------------------------------------
+struct PerDeviceLaunch {
+  bool done[64] = {};
+  int n_sm[64] = {};
+};
+template <typename Kern>
+inline cudaError_t per_device_setup(Kern kern, size_t smem, PerDeviceLaunch& st, int* n_sm = nullptr) {
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return e;
+  if (dev < 0 || dev >= 64) return cudaErrorInvalidDevice;
+  if (!st.done[dev]) {
+    if (smem > 0) {
+      e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+      if (e != cudaSuccess) return e;
+    }
+    e = cudaDeviceGetAttribute(&st.n_sm[dev], cudaDevAttrMultiProcessorCount, dev);
+    if (e != cudaSuccess) return e;
+    st.done[dev] = true;
+  }
+  if (n_sm) *n_sm = st.n_sm[dev];
+  return cudaSuccess;
+}
+
+// ------------------------------------------------------------------------------------------------
 // Activation storage types.  Arithmetic is always fp32; TAct only selects how hidden activations
 // are stored in HBM between kernels (float = parity mode, bf16 = BASELINE.json's bf16 batches).
 // ------------------------------------------------------------------------------------------------

@@ -142,12 +142,9 @@ cudaError_t launch_dft_fwd(const void* x, void* xm, int batch, float s0, float s
   }
   auto kern = minb == 4 ? dft_fwd_kernel<TAct, 4> : (minb == 5 ? dft_fwd_kernel<TAct, 5> : dft_fwd_kernel<TAct, 6>);
   constexpr size_t smem = sizeof(DftSmem<TAct>);
-  static bool configured = false;  // per-instantiation
-  if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    configured = true;
-  }
+  static PerDeviceLaunch pd[3];  // per instantiation and compile-time occupancy variant
+  cudaError_t e0 = per_device_setup(kern, smem, pd[minb - 4]);
+  if (e0 != cudaSuccess) return e0;
   const int n_ctas = batch * kC / kDftPlanes;
   return launch_chained(kern, dim3(n_ctas), dim3(kDftThreads), smem, stream, static_cast<const TAct*>(x),
                         static_cast<float2*>(xm), s0, s1);

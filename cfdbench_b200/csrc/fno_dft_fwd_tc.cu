@@ -383,20 +383,20 @@ static cudaError_t td_ensure_table(const unsigned char** out, cudaStream_t strea
   return cudaSuccess;
 }
 
+void dft_fwd_tc_release(int dev) {
+  if (dev >= 0 && dev < 64 && g_td_table[dev] != nullptr) {
+    cudaFree(g_td_table[dev]);
+    g_td_table[dev] = nullptr;
+  }
+}
+
 cudaError_t launch_dft_fwd_tc(const void* x, void* xm, int batch, float s0, float s1, cudaStream_t stream) {
   auto kern = dft_fwd_tc_kernel;
   constexpr size_t smem = sizeof(TdSmem);
-  static bool configured = false;
-  static int n_sm = 0;
-  if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    int dev = 0;
-    cudaGetDevice(&dev);
-    e = cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
-    if (e != cudaSuccess) return e;
-    configured = true;
-  }
+  static PerDeviceLaunch pd;
+  int n_sm = 0;
+  cudaError_t e0 = per_device_setup(kern, smem, pd, &n_sm);
+  if (e0 != cudaSuccess) return e0;
   const unsigned char* table = nullptr;
   cudaError_t e = td_ensure_table(&table, stream);
   if (e != cudaSuccess) return e;

@@ -251,17 +251,10 @@ __global__ void __launch_bounds__(kMxThreads, 1)
 cudaError_t launch_mode_mix(const void* xm, const void* wop, void* ym, void* ym_img, int batch, cudaStream_t stream) {
   auto kern = mode_mix_tc_kernel;
   constexpr size_t smem = sizeof(MxSmem);
-  static bool configured = false;
-  static int n_sm = 0;
-  if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    int dev = 0;
-    cudaGetDevice(&dev);
-    e = cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
-    if (e != cudaSuccess) return e;
-    configured = true;
-  }
+  static PerDeviceLaunch pd;
+  int n_sm = 0;
+  cudaError_t e0 = per_device_setup(kern, smem, pd, &n_sm);
+  if (e0 != cudaSuccess) return e0;
   const int n_btiles = (batch + kMxM - 1) / kMxM;
   const int n_tiles = kModes * n_btiles;
   const int grid = n_tiles < 2 * n_sm ? (n_tiles + 1) / 2 : n_sm;

@@ -242,17 +242,10 @@ cudaError_t launch_project_tc(const void* a, const float* w1, const float* b1, c
                               const float* mask, float* preds, int batch, cudaStream_t stream) {
   auto kern = project_tc_kernel<TAct>;
   constexpr size_t smem = sizeof(PtSmem) + 128;
-  static bool configured = false;
-  static int n_sm = 0;
-  if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    int dev = 0;
-    cudaGetDevice(&dev);
-    e = cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
-    if (e != cudaSuccess) return e;
-    configured = true;
-  }
+  static PerDeviceLaunch pd;
+  int n_sm = 0;
+  cudaError_t e0 = per_device_setup(kern, smem, pd, &n_sm);
+  if (e0 != cudaSuccess) return e0;
   const int n_tiles = batch * kPtTilesPerSample;
   const int grid = n_tiles < n_sm ? n_tiles : n_sm;
   return launch_chained(kern, dim3(grid), dim3(kPtThreads), smem, stream, static_cast<const TAct*>(a), w1, b1, w2, b2,

@@ -69,6 +69,9 @@ typedef struct fno_workspace {
 } fno_workspace;
 
 int fno_version(void);
+/* Frees what the library itself owns on the CURRENT device (constant operand tables built on first use, events of the
+ * chunked host path); they are rebuilt on demand.  Everything else is caller-owned.  Synchronises the device. */
+int fno_destroy(void);
 const char* fno_last_error(void);
 /* bytes of one activation buffer / one mode buffer for batch B */
 size_t fno_act_bytes(int batch, int act_dtype);

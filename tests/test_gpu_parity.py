@@ -305,6 +305,22 @@ def test_rollout_matches_reference_golden(name):
     assert rel(one[1].cpu().numpy(), gold[1][:1]) < 10 * TOL
 
 
+def test_destroy_releases_library_tables_and_they_are_rebuilt(lib):
+    """fno_destroy frees the constant operand tables / events the library owns on this device; the next call rebuilds them."""
+    from cfdbench_b200 import _lib
+    g, sd, batch, p = load_case("cavity_b2_gain200")
+    tb = {k: torch.from_numpy(v).cuda() for k, v in batch.items() if k != "label"}
+    outs = []
+    for act in ("float32", "bfloat16"):
+        m = make_model(sd, p, act_dtype=act)
+        m.graph_rollout = False
+        with torch.no_grad():
+            a = m.generate(tb["inputs"], tb["case_params"], tb["mask"])
+            _lib.check(lib.fno_destroy(), "fno_destroy")
+            b = m.generate(tb["inputs"], tb["case_params"], tb["mask"])
+        assert torch.equal(a, b), act
+
+
 def test_host_rollout_and_graph_rollout_equal_device_rollout():
     g, sd, batch, p = load_case("cylinder_b2_gain200")
     m = make_model(sd, p)
