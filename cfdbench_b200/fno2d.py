@@ -165,7 +165,12 @@ class Fno2d(AutoCfdModel):
         self.graph_rollout = True
         self.fused_block = True  # bf16 storage, inference: inv_kx + block_tc replaced by block_fused_kernel
         self.max_graphs = 8
-        self.host_chunks = 4  # batch chunks of the pipelined host-tensor rollout path (upload | kernels | download)
+        # host-tensor single step (bench.py's e2e), measured at B=256 bf16 (tools/e2e_sweep.py): staged copies on three
+        # streams over 2 batch chunks 0.753 ms, over 4 chunks 0.842 ms (chunks of 64 run the 14 kernels at their fixed
+        # costs); kernels reading / writing the pinned host buffers directly 0.796 ms (1 chunk) / 0.815 / 0.881 ms
+        self.host_chunks = 2
+        self.host_zero_copy = False  # opt-in: lift reads the pinned frame, project writes the pinned result directly
+        self.zero_copy_chunks = 2
         self._graphs: dict = {}
 
     # ------------------------------------------------------------------------------------ plumbing
@@ -531,6 +536,43 @@ class Fno2d(AutoCfdModel):
         seq.copy_(s_seq)
         return seq
 
+    def _step_host_zero_copy(self, inputs, case_params, mask3, out, pk) -> Tensor:
+        """One step with PINNED host frames and no staging copies: the lift kernel reads the frame straight from host
+        memory and the project kernel writes the prediction straight into the caller's pinned result tensor (unified
+        addressing: a pinned allocation is device-accessible at the same address), so both transfers ride inside the
+        first / last kernel of the step instead of in front of / behind it.  The batch is cut into `zero_copy_chunks`
+        halves on two streams: while one half runs its Fourier blocks the other half's lift (PCIe-bound) runs.  Mask and
+        case parameters stay cached on the device between calls."""
+        lib = _lib.load()
+        b, dev = inputs.shape[0], self.device
+        cur = torch.cuda.current_stream(dev)
+        n_chunks = self.zero_copy_chunks if b % self.zero_copy_chunks == 0 and b // self.zero_copy_chunks >= 8 else 1
+        cb = b // n_chunks
+        key = ("host_zero_copy", b, n_chunks)
+        ent = self._ws_cache.get(key)
+        if ent is None:
+            ent = dict(d_mask=torch.empty(b, 1, H, W, dtype=torch.float32, device=dev),
+                       d_cp=torch.empty(b, max(self.n_case_params, 1), dtype=torch.float32, device=dev),
+                       streams=[torch.cuda.Stream(device=dev) for _ in range(n_chunks)], inv_key=None)
+            self._ws_cache[key] = ent
+        inv_key = (mask3.data_ptr(), mask3._version, case_params.data_ptr(), case_params._version, tuple(mask3.shape))
+        if ent["inv_key"] != inv_key:
+            ent["d_mask"].view(b, H, W).copy_(mask3, non_blocking=True)
+            if self.n_case_params > 0:
+                ent["d_cp"][:, :self.n_case_params].copy_(case_params, non_blocking=True)
+            ent["inv_key"] = inv_key
+        out2 = out.view(b, self.out_chan, H, W)
+        for c, st in enumerate(ent["streams"]):
+            st.wait_stream(cur)
+            ws, _ = self._workspace(cb, slot=1 + c)
+            lo = c * cb
+            _lib.check(lib.fno_forward(C.byref(pk["struct"]), inputs[lo:lo + cb].data_ptr(), ent["d_mask"][lo:lo + cb].data_ptr(),
+                                       ent["d_cp"][lo:lo + cb].data_ptr(), out2[lo:lo + cb].data_ptr(), C.byref(ws), cb,
+                                       self._act_code(), C.c_void_p(st.cuda_stream)), "fno_forward")
+        for st in ent["streams"]:
+            st.synchronize()
+        return out
+
     def _rollout_host(self, inputs: Tensor, case_params: Tensor, mask: Tensor, steps: int) -> Tensor:
         """Host tensors in -> host tensors out; the result is a tensor the caller OWNS (fresh pinned memory from torch's
         caching host allocator, never a view of a reused buffer -- the reference returns fresh tensors too).
@@ -553,6 +595,8 @@ class Fno2d(AutoCfdModel):
         dev = self.device
         cur = torch.cuda.current_stream(dev)
         out = torch.empty(steps, b, self.out_chan, H, W, dtype=torch.float32, pin_memory=True)
+        if steps == 1 and self.host_zero_copy and inputs.is_pinned() and b >= 8:
+            return self._step_host_zero_copy(inputs, case_params, mask3, out, pk)
         n_chunks = self.host_chunks if (steps == 1 and b >= 128 and b % self.host_chunks == 0) else 1
         if n_chunks == 1:
             key = ("host_io", b, steps)
