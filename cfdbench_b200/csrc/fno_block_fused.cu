@@ -117,8 +117,28 @@ __global__ void __launch_bounds__(kFzThreads, 1)
   const int tid = threadIdx.x, lane = tid & 31, warp = tc::warp_index_uniform();
 
   const int first = blockIdx.x, stride = gridDim.x;
-  const int n_mine = (first < n_units) ? (n_units - first + stride - 1) / stride : 0;
-  auto unit_of = [&](int k) { return first + k * stride; };   // unit u = 2 * sample + half
+  // Work items of this CTA: `n_full` whole units (u = first + k * stride; unit u = 2 * sample + half image), then the units
+  // of the last, incomplete round.  When at most half of the CTAs would get one of those, each of them is SPLIT between two
+  // CTAs (rows 0-15 / 16-31 of the half image = super-tiles 0-3 / 4-7; both run the unit's GEMM1, on 32 columns only), so
+  // the makespan is 3.5 instead of 4 units at B = 256 (512 units on 148 SMs).
+  const int n_full = n_units / stride, n_rem = n_units % stride;
+  int ex_u = -1, ex_s0 = 0, ex_ns = 0;   // extra item: unit, first unit-local super-tile, number of super-tiles
+  if (n_rem > 0) {
+    if (2 * n_rem <= stride) {
+      if (first < 2 * n_rem) { ex_u = n_full * stride + first % n_rem; ex_s0 = (first / n_rem) * (kFzSPU / 2); ex_ns = kFzSPU / 2; }
+    } else if (first < n_rem) {
+      ex_u = n_full * stride + first;
+      ex_ns = kFzSPU;
+    }
+  }
+  const int n_mine = n_full + (ex_ns > 0 ? 1 : 0);        // items
+  const int n_super_all = n_full * kFzSPU + ex_ns;         // super-tiles of all items
+  auto unit_of = [&](int k) { return k < n_full ? first + k * stride : ex_u; };
+  auto item_s0 = [&](int k) { return k < n_full ? 0 : ex_s0; };
+  auto item_ns = [&](int k) { return k < n_full ? kFzSPU : ex_ns; };
+  // global super-tile S of this CTA -> (unit, unit-local super-tile)
+  auto super_unit = [&](int S) { return S < n_full * kFzSPU ? first + (S / kFzSPU) * stride : ex_u; };
+  auto super_local = [&](int S) { return S < n_full * kFzSPU ? S % kFzSPU : ex_s0 + (S - n_full * kFzSPU); };
 
   // ---------------------------------------------------------------- prologue (weights / constant tables only)
   if (tid == 0) {
@@ -199,19 +219,20 @@ __global__ void __launch_bounds__(kFzThreads, 1)
       mbar_wait(&sm.d1_full, k & 1);
       tc::fence_after_thread_sync();
       if (tid == 0) FZ_T(0, k * kFzSPU, 1);
+      const int hh_begin = item_s0(k) / 4, hh_end = (item_s0(k) + item_ns(k)) / 4;
 #pragma unroll 1
-      for (int hh = 0; hh < 2; ++hh) {
+      for (int hh = hh_begin; hh < hh_end; ++hh) {
         float v[32];
         tc::tmem_ld32(tmem + kFzColD1 + mt * 64 + hh * 32 + lane_base, v);
-        if (tid == 0) FZ_T(0, k * kFzSPU + hh * 4, 2);
-        if (hh == 1) {   // D1 fully read: the next unit's GEMM1 may overwrite it
+        if (tid == 0) FZ_T(0, k * kFzSPU + (hh - hh_begin) * 4, 2);
+        if (hh == hh_end - 1) {   // D1 fully read: the next item's GEMM1 may overwrite it
           tc::fence_before_thread_sync();
           __syncwarp();
           if (lane == 0) mbar_arrive(&sm.d1_free);
         }
 #pragma unroll
         for (int s4 = 0; s4 < 4; ++s4) {
-          const int S = k * kFzSPU + hh * 4 + s4;
+          const int S = k * kFzSPU + (hh - hh_begin) * 4 + s4;   // all items but the last have kFzSPU super-tiles
           const int ss = S % kFzR;
           if (tid == 0) FZ_T(0, S, 3);
           if (S >= kFzR) mbar_wait(&sm.slot_free[fz_bar(S - kFzR)], fz_phase(S - kFzR));   // previous user of the slot
@@ -244,11 +265,11 @@ __global__ void __launch_bounds__(kFzThreads, 1)
   else if (warp < kFzConvWarps + kFzEpiWarps) {
     const int q = warp & 3, grp = (warp - kFzConvWarps) >> 2;
     const uint32_t lane_base = static_cast<uint32_t>(q * 32) << 16;
-    const int n_super = n_mine * kFzSPU;
+    const int n_super = n_super_all;
     const bool odd = lane & 1;
     for (int S = grp; S < n_super; S += 2) {
       const int ss = S % kFzR;
-      const int u = unit_of(S / kFzSPU), t0 = (S % kFzSPU) * kFzTS;
+      const int u = super_unit(S), t0 = super_local(S) * kFzTS;
       if ((warp & 3) == 0 && lane == 0) FZ_T(1, S, 0);
       mbar_wait(&sm.d2_full[fz_bar(S)], fz_phase(S));
       tc::fence_after_thread_sync();
@@ -290,7 +311,7 @@ __global__ void __launch_bounds__(kFzThreads, 1)
       const uint32_t w_s = tc::smem_addr(sm.w);
       constexpr uint32_t idesc_e = tc::make_idesc_tf32(128, 32) | kBMajorMN;
       constexpr uint32_t idesc_c = fz_idesc_bf16(128, 32) | kAMajorMN;
-      const int n_super = n_mine * kFzSPU;
+      const int n_super = n_super_all;
 #pragma unroll 1
       for (int S = warp - kFzMmaWarp; S < n_super; S += 2) {
         const int ss = S % kFzR;
@@ -330,10 +351,15 @@ __global__ void __launch_bounds__(kFzThreads, 1)
   else if (warp == kFzG1Warp) {
     if (tc::elect_one()) {
       const uint32_t f_hi = tc::smem_addr(sm.f), f_lo = f_hi + kFzFBytes / 2;
-      constexpr uint32_t idesc_g1 = tc::make_idesc_tf32(128, 64) | kAMajorMN;
+      constexpr uint32_t idesc_g64 = tc::make_idesc_tf32(128, 64) | kAMajorMN;
+      constexpr uint32_t idesc_g32 = tc::make_idesc_tf32(128, 32) | kAMajorMN;
 #pragma unroll 1
       for (int k = 0; k < n_mine; ++k) {
         const uint32_t neg = (unit_of(k) & 1) ? kANegate : 0u;   // second half image: odd kx change sign
+        // a split item needs only the 32 columns (16 rows x re|im) of its rows: N = 32 at column / B-row offset 32 hh
+        const bool half_item = item_ns(k) < kFzSPU;
+        const uint32_t col0 = half_item ? static_cast<uint32_t>(item_s0(k) / 4) * 32u : 0u;
+        const uint32_t idesc_g1 = half_item ? idesc_g32 : idesc_g64;
         if (k >= 1) {   // the converters have pulled the previous unit's D1 out of tensor memory (at their tile 8)
           mbar_wait(&sm.d1_free, (k - 1) & 1);
           tc::fence_after_thread_sync();
@@ -347,7 +373,7 @@ __global__ void __launch_bounds__(kFzThreads, 1)
           tc::fence_after_thread_sync();
           FZ_T(3, k * 8 + st, 1);
           const uint32_t a_hi = tc::smem_addr(sm.y[slot]), a_lo = a_hi + kFzYStage / 2;
-          const uint32_t d = tmem + kFzColD1 + mt * 64;
+          const uint32_t d = tmem + kFzColD1 + mt * 64 + col0;
           const uint32_t idesc = idesc_g1 | (par ? neg : 0u);
 #pragma unroll
           for (int pass = 0; pass < 3; ++pass) {
@@ -356,7 +382,7 @@ __global__ void __launch_bounds__(kFzThreads, 1)
 #pragma unroll
             for (int ks = 0; ks < 3; ++ks) {
               const uint64_t da = fz_desc_sw128_32(a_s + ks * 1024, 3072, 512);
-              const uint64_t db = tc::make_smem_desc(b_s + (3 * par + ks) * 2048, 1024, 128);
+              const uint64_t db = tc::make_smem_desc(b_s + (3 * par + ks) * 2048 + (col0 >> 3) * 128, 1024, 128);
               fz_mma_tf32_ss(d, da, db, idesc, (par | pass | ks) ? 1u : 0u);
             }
           }
@@ -371,10 +397,10 @@ __global__ void __launch_bounds__(kFzThreads, 1)
   // ================================================================ producers
   else if (warp == kFzProdWarp) {
     if (lane == 0) {          // x tiles: two {64 px, 32 ch} boxes per tile, kFzTS tiles per super-slot
-      const int n_super = n_mine * kFzSPU;
+      const int n_super = n_super_all;
       for (int S = 0; S < n_super; ++S) {
         const int ss = S % kFzR;
-        const int u = unit_of(S / kFzSPU), t0 = (S % kFzSPU) * kFzTS;
+        const int u = super_unit(S), t0 = super_local(S) * kFzTS;
         const int b = u >> 1;
         if (S >= kFzR) mbar_wait(&sm.slot_free[fz_bar(S - kFzR)], fz_phase(S - kFzR));
         uint64_t* rdy = &sm.ready[fz_bar(S)];
@@ -520,7 +546,9 @@ cudaError_t launch_block_fused(const void* ym_img, const void* x, const float* w
   e = fz_make_map(x, batch, &map);
   if (e != cudaSuccess) return e;
   const int n_units = 2 * batch;
-  const int grid = n_units < g_fz[dev].n_sm ? n_units : g_fz[dev].n_sm;
+  // few units: two CTAs per unit (the kernel splits a unit's rows between them)
+  const int n_sm = g_fz[dev].n_sm;
+  const int grid = 2 * n_units <= n_sm ? 2 * n_units : (n_units < n_sm ? n_units : n_sm);
   return launch_chained(block_fused_kernel, dim3(grid), dim3(kFzThreads), sizeof(FzSmem), stream, map,
                         static_cast<const unsigned char*>(ym_img), w0t, bias, static_cast<const float*>(g_fz[dev].etab),
                         static_cast<const float*>(g_fz[dev].ftab), static_cast<__nv_bfloat16*>(out), n_units);
