@@ -1,4 +1,5 @@
 // extern "C" surface of libcfdbench_b200.so (declared in include/cfdbench_b200.h).
+#include <stdlib.h>
 #include <stdio.h>
 #include <string.h>
 
@@ -156,6 +157,15 @@ int fno_lift_fwd(const float* inputs, const float* mask, const float* case_param
 
 int fno_spectral_dft_fwd(const void* act_in, void* xm, int batch, int act_dtype, float s0, float s1, void* stream) {
   if (!act_in || !xm || batch <= 0 || bad_dtype(act_dtype)) return fail(kErrArg, "fno_spectral_dft_fwd: bad argument");
+  if (act_dtype == FNO_ACT_BF16) {
+    // bf16 planes: the two-GEMM tensor-core kernel (fno_dft_fwd_tc.cu); FNO_DFT_TC=0 selects the register-FFT kernel
+    // (an A/B switch for measurements, read once)
+    static const bool use_tc = [] { const char* v = getenv("FNO_DFT_TC"); return !(v && v[0] == '0'); }();
+    if (use_tc) {
+      FNO_CUDA(launch_dft_fwd_tc(act_in, xm, batch, s0, s1, S(stream)), "dft_fwd_tc_kernel");
+      return kOk;
+    }
+  }
   cudaError_t e = act_dtype == FNO_ACT_F32 ? launch_dft_fwd<float>(act_in, xm, batch, s0, s1, S(stream))
                                            : launch_dft_fwd<__nv_bfloat16>(act_in, xm, batch, s0, s1, S(stream));
   FNO_CUDA(e, "dft_fwd_kernel");
