@@ -60,12 +60,19 @@ constexpr uint32_t kFzColD2 = 288;   // kFzR x kFzTS x 32
 // clock64() at the hand-off points of every role: trace[(role * 256 + T) * 8 + event].
 #ifdef FNO_FZ_TRACE
 __device__ long long* g_fz_trace = nullptr;
+// The pointer is read ONCE per thread (fz_tr): re-reading the global for every stamp costs an L2 round trip (~450 cycles)
+// that the stamps of a single-thread role then mostly measure (tools/mbar_probe.cu: a completed mbarrier wait is 46 cycles).
 #define FZ_T(role, T, ev)                                                                          \
   do {                                                                                             \
-    if (g_fz_trace != nullptr && blockIdx.x == 0 && (T) < 256) g_fz_trace[((role) * 256 + (T)) * 8 + (ev)] = clock64(); \
+    if (fz_tr != nullptr && blockIdx.x == 0 && (T) < 256) fz_tr[((role) * 256 + (T)) * 8 + (ev)] = clock64(); \
   } while (0)
+// knock-out experiments (results are wrong): 1 no conv MMAs, 2 no E MMAs, 4 no GEMM1 MMAs, 8 no converter stores,
+// 16 no GELU, 32 no output stores
+__device__ int g_fz_knock = 0;
+#define FZ_KNOCK(bit) ((fz_knock & (bit)) != 0)
 #else
 #define FZ_T(role, T, ev) do { } while (0)
+#define FZ_KNOCK(bit) false
 #endif
 
 struct FzSmem {
@@ -112,7 +119,9 @@ __global__ void __launch_bounds__(kFzThreads, 1)
   FzSmem& sm = *reinterpret_cast<FzSmem*>(smem_raw);
   if ((smem_u32(smem_raw) & 1023u) != 0) __trap();
 #ifdef FNO_FZ_TRACE
-  if (g_fz_trace != nullptr && threadIdx.x == 0) g_fz_trace[4 * 256 * 8 + blockIdx.x * 4 + 0] = clock64();
+  long long* const fz_tr = g_fz_trace;
+  const int fz_knock = g_fz_knock;
+  if (fz_tr != nullptr && threadIdx.x == 0) fz_tr[4 * 256 * 8 + blockIdx.x * 4 + 0] = clock64();
 #endif
   const int tid = threadIdx.x, lane = tid & 31, warp = tc::warp_index_uniform();
 
@@ -194,7 +203,7 @@ __global__ void __launch_bounds__(kFzThreads, 1)
   __syncthreads();
   tc::fence_after_thread_sync();
 #ifdef FNO_FZ_TRACE
-  if (g_fz_trace != nullptr && threadIdx.x == 0) g_fz_trace[4 * 256 * 8 + blockIdx.x * 4 + 1] = clock64();
+  if (fz_tr != nullptr && threadIdx.x == 0) fz_tr[4 * 256 * 8 + blockIdx.x * 4 + 1] = clock64();
 #endif
   pdl_wait();   // ym_img and x come from the previous kernels of the chain
   pdl_launch_dependents();
@@ -246,6 +255,7 @@ __global__ void __launch_bounds__(kFzThreads, 1)
               if ((r & 1) && ky == 0) z = bias_o;   // Im of the ky = 0 column is dropped by C2R; the row carries the bias
               float hi, lo;
               tc::split_tf32(z, hi, lo);
+              if (FZ_KNOCK(8)) continue;
               *reinterpret_cast<float*>(slot + roff[r]) = hi;
               *reinterpret_cast<float*>(slot + 6144 + roff[r]) = lo;
             }
@@ -290,13 +300,13 @@ __global__ void __launch_bounds__(kFzThreads, 1)
         __nv_bfloat16* dst = out + (static_cast<size_t>(b) * kC + (odd ? 1 : 0)) * kHW + px;
 #pragma unroll
         for (int c = 0; c < 32; c += 2) {
-          const float2 g = gelu_erf2(make_float2(v[c], v[c + 1]));
+          const float2 g = FZ_KNOCK(16) ? make_float2(v[c], v[c + 1]) : gelu_erf2(make_float2(v[c], v[c + 1]));
           const __nv_bfloat162 pk = __float22bfloat162_rn(g);                    // (channel c, channel c+1) of my pixel
           const uint32_t mine = *reinterpret_cast<const uint32_t*>(&pk);
           const uint32_t other = __shfl_xor_sync(0xffffffffu, mine, 1);
           // even lane: (my c, neighbour's c);  odd lane: (neighbour's c+1, my c+1)
           const uint32_t pair = odd ? __byte_perm(other, mine, 0x7632) : __byte_perm(mine, other, 0x5410);
-          *reinterpret_cast<uint32_t*>(dst + static_cast<size_t>(c) * kHW) = pair;
+          if (!FZ_KNOCK(32)) *reinterpret_cast<uint32_t*>(dst + static_cast<size_t>(c) * kHW) = pair;
         }
       }
       if ((warp & 3) == 0 && lane == 0) FZ_T(1, S, 3);
@@ -327,6 +337,7 @@ __global__ void __launch_bounds__(kFzThreads, 1)
           for (int pc = 0; pc < 3; ++pc)
 #pragma unroll
             for (int ks = 0; ks < 2; ++ks)
+              if (!FZ_KNOCK(1) || (pc | ks) == 0)
               fz_mma_f16_ss(d, fz_desc_sw128(x_s + ks * 2048, 4096, 1024),
                             tc::make_smem_desc(w_s + pc * 2048 + ks * 1024, 512, 128), idesc_c, (pc | ks) ? 1u : 0u);
           const uint32_t z_hi = tc::smem_addr(sm.bt[ss][i]), z_lo = z_hi + 6144;
@@ -336,6 +347,7 @@ __global__ void __launch_bounds__(kFzThreads, 1)
             const uint32_t b_s = (pass == 2) ? z_lo : z_hi;
 #pragma unroll
             for (int ks = 0; ks < 6; ++ks)
+              if (!FZ_KNOCK(2))
               fz_mma_tf32_ts(d, a_t + ks * 8, fz_desc_sw128_32(b_s + ks * 1024, 0, 512), idesc_e, 1u);
           }
         }
@@ -383,7 +395,7 @@ __global__ void __launch_bounds__(kFzThreads, 1)
             for (int ks = 0; ks < 3; ++ks) {
               const uint64_t da = fz_desc_sw128_32(a_s + ks * 1024, 3072, 512);
               const uint64_t db = tc::make_smem_desc(b_s + (3 * par + ks) * 2048 + (col0 >> 3) * 128, 1024, 128);
-              fz_mma_tf32_ss(d, da, db, idesc, (par | pass | ks) ? 1u : 0u);
+              if (!FZ_KNOCK(4)) fz_mma_tf32_ss(d, da, db, idesc, (par | pass | ks) ? 1u : 0u);
             }
           }
           tc::mma_commit(&sm.y_empty[slot]);
@@ -435,7 +447,7 @@ __global__ void __launch_bounds__(kFzThreads, 1)
   tc::fence_before_thread_sync();
   __syncthreads();
 #ifdef FNO_FZ_TRACE
-  if (g_fz_trace != nullptr && threadIdx.x == 0) g_fz_trace[4 * 256 * 8 + blockIdx.x * 4 + 2] = clock64();
+  if (fz_tr != nullptr && threadIdx.x == 0) fz_tr[4 * 256 * 8 + blockIdx.x * 4 + 2] = clock64();
 #endif
   if (warp == kFzMmaWarp) tc::tmem_dealloc<512>(tmem);
 }
@@ -517,6 +529,7 @@ static cudaError_t fz_ensure(int dev, cudaStream_t stream) {
 }
 
 #ifdef FNO_FZ_TRACE
+extern "C" int fno_debug_fused_knock(int bits) { return cudaMemcpyToSymbol(g_fz_knock, &bits, sizeof(bits)) == cudaSuccess ? 0 : 2; }
 extern "C" int fno_debug_fused_trace(void* p) {
   long long* q = static_cast<long long*>(p);
   return cudaMemcpyToSymbol(g_fz_trace, &q, sizeof(q)) == cudaSuccess ? 0 : 2;

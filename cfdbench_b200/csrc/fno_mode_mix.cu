@@ -3,84 +3,78 @@
 // Replaces the two torch.einsum("bixy,ioxy->boxy") corner products plus the zero-filled
 // (B,32,64,33) cfloat buffer of the reference (src/models/fno/fno2d.py:54-57, 65-78).
 //
-// Modes are stored mode-major (xm[k][b][c], written that way by dft_fwd_kernel), so the 128 rows of a tile are one
-// contiguous 32 KB block; with the sample-major layout the same rows sat 73,728 B apart and both this kernel and its
-// CUDA-core predecessor were bound by that access pattern (~20 us per launch at B=256 whatever the arithmetic).
-// For one mode k the mix over a tile of 128 samples is a real GEMM on the interleaved complex64 rows exactly
-// as they sit in memory:
+// Modes are stored mode-major (xm[k][b][c], written that way by the forward DFT kernels), so the 128 rows of a tile are
+// one contiguous 32 KB block.  For one mode k the mix over a tile of 128 samples is a real GEMM on the interleaved
+// complex64 rows exactly as they sit in memory:
 //     D[128 samples][64 = (o, re|im)] = A[128][64 = (i, re|im)] * B_k^T         (tcgen05.mma kind::tf32, K = 64)
 //     B_k[(o,re)][(i,re)] = Wre,  B_k[(o,re)][(i,im)] = -Wim,  B_k[(o,im)][(i,re)] = Wim,  B_k[(o,im)][(i,im)] = Wre
-// run as 3xTF32 (hi*hi + lo*hi + hi*lo).  The B operand of every mode is prepared once per weight update
-// (pack_mix_operand_kernel: real-expanded, split into tf32 hi/lo, laid out as the K-major UMMA image) and arrives
-// with ONE 32 KB bulk copy per tile; the activations-side rows are prefetched into registers one tile ahead
-// (two 256-byte rows per warp instruction), split and stored as the A operand.  The A operand's K-direction core
-// matrix stride (LBO) is skewed by 16 B so that the 16-byte stores of lanes running along K are bank-conflict free.
-// Persistent CTA = two independent 256-thread pipelines, accumulators double-buffered in TMEM; the epilogue writes
-// 128 contiguous bytes per thread.  With the conj-transposed pack the same kernel is the adjoint mix of the
-// backward pass (Xbar[b,i,k] = sum_o G[b,o,k] conj(W[i,o,k])).
+// run as 3xTF32.  The B operand of every mode is prepared once per weight update (pack_mix_operand_*_kernel:
+// real-expanded, split into tf32 hi/lo, laid out as the K-major UMMA image) and arrives with ONE 32 KB bulk copy per mode.
 //
-// (The CUDA-core version of this phase -- weights in registers, FFMA2 -- is in the history up to commit 73b34cc:
-// 20.7 us per launch at B=256 against the ~6 us its 40 MB of HBM traffic need.)
+// Warp-specialised (round 2; round 1's version staged A through registers in two 256-thread pipelines and was
+// latency-bound at ~2 tiles per pipeline: 19 us against the ~10 us its 66 MB need):
+//   * work item = one MODE (all its sample tiles): B_k is fetched once per mode, 288 items on 148 persistent CTAs;
+//   * warp 16 lane 0 -- producer: the A tile is the raw fp32 block itself, dropped by TMA (two {32 floats, 128 rows}
+//     boxes, 128-byte swizzle) into a 4-slot ring as a K-major operand.  At B = 256 the ring holds ALL the tiles of a CTA,
+//     so every load of the kernel is in flight from the first microsecond;
+//   * the tensor core truncates what it reads to tf32, so the raw tile IS the hi operand; warps 0-7 compute the lo part
+//     (x - trunc(x), exact, then rounded) element by element at the SAME swizzled offsets into a second buffer;
+//   * warp 17 -- MMA issue: A_raw x B_hi, A_raw x B_lo (16 MMAs, need only the TMA data) then A_lo x B_hi (8);
+//     4 accumulators of 64 columns, so the epilogue of a tile never holds up the next tile's MMAs;
+//   * warps 8-15 -- epilogue: mode-major ym rows (fp32 path / backward) or the per-sample operand image of
+//     block_fused_kernel's GEMM1 (tf32 hi/lo split here, 256-bit stores).
+// With the conj-transposed pack the same kernel is the adjoint mix of the backward pass
+// (Xbar[b,i,k] = sum_o G[b,o,k] conj(W[i,o,k])).
 #include "fno_common.cuh"
 #include "tc_common.cuh"
+#include "tc_tma.cuh"
 
 namespace fno {
 
-constexpr int kMxThreads = 512;  // two independent 256-thread tile pipelines
-constexpr int kMxGroup = 256;
 constexpr int kMxM = 128;        // samples per tile
 constexpr int kMxK = 2 * kC;     // 64 real (i, re|im)
 constexpr int kMxN = 2 * kC;     // 64 real (o, re|im)
-constexpr uint32_t kMxLboA = (kMxM / 8) * 128 + 16;  // 2064: skewed K-direction core-matrix stride of A
 constexpr uint32_t kMxLboB = (kMxN / 8) * 128;       // 1024
-constexpr int kMxAFloats = (kMxK / 4) * kMxLboA / 4; // 8256
 constexpr int kMxBFloats = kMxN * kMxK;              // 4096 per image (hi or lo)
 constexpr int kMxOperandFloats = 2 * kMxBFloats;     // per mode: hi image then lo image (32 KB)
-constexpr int kMxReps = (kMxM * kMxK / 4) / kMxGroup;  // 8 float4 per thread per tile
+constexpr int kMxConvWarps = 8, kMxEpiWarps = 8;
+constexpr int kMxProdWarp = 16, kMxMmaWarp = 17;
+constexpr int kMxThreads = 18 * 32;
+constexpr int kMxRing = 4;                           // A slots (and accumulators)
+constexpr uint32_t kMxABytes = kMxM * kMxK * 4;      // 32,768 B per tile: two K halves of 128 rows x 128 B
+constexpr uint32_t kMxBBytes = kMxOperandFloats * 4; // 32,768 B per mode
+
+// Optional timeline trace (-DFNO_FZ_TRACE build, tools/trace_mix.py): CTA 0 stamps clock64() at the hand-off points,
+// trace[(role * 16 + tile) * 8 + event]; per-CTA clock / globaltimer stamps follow at 4 * 16 * 8.
+#ifdef FNO_FZ_TRACE
+__device__ long long* g_mx_trace = nullptr;
+#define MX_T(role, T, ev)                                                                          \
+  do {                                                                                             \
+    if (mx_tr != nullptr && blockIdx.x == 0 && (T) < 16) mx_tr[((role) * 16 + (T)) * 8 + (ev)] = clock64(); \
+  } while (0)
+#define MX_CTA(ev)                                                                                 \
+  do {                                                                                             \
+    if (mx_tr != nullptr && threadIdx.x == 0) {                                                    \
+      mx_tr[4 * 16 * 8 + blockIdx.x * 4 + (ev)] = clock64();                                       \
+      long long gt_;                                                                               \
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt_));                                      \
+      mx_tr[4 * 16 * 8 + 148 * 4 + blockIdx.x * 4 + (ev)] = gt_;                                   \
+    }                                                                                              \
+  } while (0)
+#else
+#define MX_T(role, T, ev) do { } while (0)
+#define MX_CTA(ev) do { } while (0)
+#endif
 
 struct MxSmem {
-  alignas(128) float a_hi[2][kMxAFloats];       // [pipeline] 2 x 33,024 B
-  alignas(128) float a_lo[2][kMxAFloats];
-  alignas(128) float b[2][kMxOperandFloats];    // [pipeline] 2 x 32 KB, bulk-copied per tile
-  alignas(8) uint64_t mma_bar[2][2];
-  alignas(8) uint64_t b_bar[2];
+  alignas(1024) unsigned char a[kMxRing][kMxABytes];   // raw fp32 tiles (TMA, 128B swizzle): the hi operand
+  alignas(1024) unsigned char a_lo[kMxABytes];         // lo operand of the tile being multiplied
+  alignas(1024) float b[2][kMxOperandFloats];          // [mode parity] hi | lo images
+  alignas(8) uint64_t a_full[kMxRing], a_free[kMxRing], d_full[kMxRing], d_free[kMxRing];
+  uint64_t b_full[2], b_free[2];
+  uint64_t lo_ready, lo_free;
   uint32_t tmem_base;
 };
-
-// float index of A element (row m, column kk) with kk a multiple of 4
-__device__ __forceinline__ uint32_t mx_a_offset(int m, int kk) {
-  return (static_cast<uint32_t>(kk >> 2) * kMxLboA + static_cast<uint32_t>(m >> 3) * 128u + static_cast<uint32_t>(m & 7) * 16u) >> 2;
-}
-
-struct MxRegs {
-  float4 v[kMxReps];  // task = rep*256 + gtid -> (row m = task >> 4, 16-byte chunk = task & 15)
-};
-
-__device__ __forceinline__ void mx_prefetch(MxRegs& r, const float4* __restrict__ xm, int k, int b0, int batch, int gtid) {
-#pragma unroll
-  for (int rep = 0; rep < kMxReps; ++rep) {
-    const int task = rep * kMxGroup + gtid;
-    const int m = task >> 4, ch = task & 15;
-    r.v[rep] = (b0 + m < batch) ? __ldg(xm + (static_cast<size_t>(k) * batch + b0 + m) * (kC / 2) + ch)
-                                : make_float4(0.f, 0.f, 0.f, 0.f);
-  }
-}
-
-__device__ __forceinline__ void mx_split_store(const MxRegs& r, float* a_hi, float* a_lo, int gtid) {
-#pragma unroll
-  for (int rep = 0; rep < kMxReps; ++rep) {
-    const int task = rep * kMxGroup + gtid;
-    const int m = task >> 4, ch = task & 15;
-    float4 hi, lo;
-    tc::split_tf32(r.v[rep].x, hi.x, lo.x);
-    tc::split_tf32(r.v[rep].y, hi.y, lo.y);
-    tc::split_tf32(r.v[rep].z, hi.z, lo.z);
-    tc::split_tf32(r.v[rep].w, hi.w, lo.w);
-    const uint32_t off = mx_a_offset(m, 4 * ch);
-    *reinterpret_cast<float4*>(a_hi + off) = hi;
-    *reinterpret_cast<float4*>(a_lo + off) = lo;
-  }
-}
 
 // 256-bit global store (sm_100: st.global.v8): the image epilogue writes 32-byte chunks of 32 different samples per warp
 // instruction, so the instruction count -- not the bytes -- is what the LSU queue sees (lg_throttle 5.0 per issue with
@@ -91,160 +85,219 @@ __device__ __forceinline__ void mx_store32(void* dst, const float* v) {
                : "memory");
 }
 
-template <int GRP>
-__device__ __forceinline__ void mx_group_barrier() {
-  asm volatile("bar.sync %0, %1;" ::"n"(GRP + 1), "n"(kMxGroup) : "memory");
-}
-
-template <int GRP>
-__device__ __forceinline__ void mx_pipeline(MxSmem& sm, const float4* __restrict__ xm, const float* __restrict__ wop,
-                                            float4* __restrict__ ym, unsigned char* __restrict__ ym_img, int batch,
-                                            int n_btiles, int n_tiles) {
-  const int tid = threadIdx.x, lane = tid & 31;
-  const int gtid = tid & (kMxGroup - 1), gwarp = tc::warp_index_uniform() & 7;
-  const uint32_t tmem_base = sm.tmem_base + GRP * (2 * kMxN);
-  constexpr uint32_t idesc = tc::make_idesc_tf32(kMxM, kMxN);
-
-  const int first = blockIdx.x, stride = gridDim.x;
-  const int n_cta = (first < n_tiles) ? (n_tiles - first + stride - 1) / stride : 0;
-  const int n_mine = (n_cta + 1 - GRP) / 2;
-  auto tile_of = [&](int it) { return first + (2 * it + GRP) * stride; };  // tile = k * n_btiles + sample tile
-
-  // epilogue of local tile `it`: warps w and w+4 share TMEM lane quadrant w & 3 (rows 32(w&3)..+31 of the tile) and
-  // take the 32-float column halves; a thread writes 128 contiguous bytes of its sample's output row
-  auto epilogue = [&](int it) {
-    const int buf = it & 1;
-    mbar_wait(&sm.mma_bar[GRP][buf], (it >> 1) & 1);
-    tc::fence_after_thread_sync();
-    const int quad = gwarp & 3, half = gwarp >> 2;
-    const int tile = tile_of(it);
-    const int k = tile / n_btiles, b = (tile % n_btiles) * kMxM + quad * 32 + lane;
-    float v[32];
-    tc::tmem_ld32(tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + buf * kMxN + half * 32, v);
-    tc::fence_before_thread_sync();
-    if (b < batch && ym_img == nullptr) {
-      float4* dst = ym + (static_cast<size_t>(k) * batch + b) * (kC / 2) + half * 8;
-#pragma unroll
-      for (int c = 0; c < 8; ++c) dst[c] = make_float4(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
-    } else if (b < batch) {
-      // Operand image of block_fused_kernel's GEMM1 (fno_block_fused.cu): per sample [hi|lo][ky/4][ky%4][48 rows][32 o]
-      // fp32, row = 24 (kxi & 1) + 2 (kxi >> 1) + (re|im), 32-byte chunks XOR-swizzled with (row & 3); tf32 hi / lo
-      // split here so the consumer is pure bulk copy + MMA.  This thread holds o = 16 half .. 16 half + 15, (re, im).
-      const int kxi = k / kM2, ky = k % kM2;
-      unsigned char* img = ym_img + static_cast<size_t>(b) * 147456 + (ky >> 2) * 24576 + (ky & 3) * 6144;
-#pragma unroll
-      for (int ri = 0; ri < 2; ++ri) {
-        const int row = 24 * (kxi & 1) + 2 * (kxi >> 1) + ri;
-#pragma unroll
-        for (int c = 0; c < 2; ++c) {
-          float hi[8], lo[8];
-#pragma unroll
-          for (int j = 0; j < 8; ++j) tc::split_tf32(v[2 * (8 * c + j) + ri], hi[j], lo[j]);
-          unsigned char* dst = img + row * 128 + (((2 * half + c) ^ (row & 3)) << 5);
-          mx_store32(dst, hi);            // one 32-byte chunk = one full sector per store instruction
-          mx_store32(dst + 73728, lo);
-        }
-      }
-    }
-  };
-
-  // Two tiles of activations are in flight in registers (at B = 256 a pipeline owns only ~2 tiles, so every
-  // load of the kernel is issued up front and the DRAM latency is paid once, not once per tile).
-  MxRegs ring[2];
-  auto prefetch_tile = [&](MxRegs& r, int it) {
-    if (it < n_mine) {
-      const int t = tile_of(it);
-      mx_prefetch(r, xm, t / n_btiles, (t % n_btiles) * kMxM, batch, gtid);
-    }
-  };
-  prefetch_tile(ring[0], 0);
-  prefetch_tile(ring[1], 1);
-
-  auto body = [&](int it, MxRegs& regs) {
-    const int buf = it & 1;
-    const int tile = tile_of(it);
-    // the single-buffered operands were last read by the MMAs of tile it-1: wait for them (normally long done)
-    if (it >= 1) mbar_wait(&sm.mma_bar[GRP][(it - 1) & 1], ((it - 1) >> 1) & 1);
-    if (it >= 1 && gwarp == 0 && tc::elect_one()) {  // this tile's B operand: one bulk copy (tile 0: kernel prologue)
-      constexpr uint32_t kBytes = kMxOperandFloats * sizeof(float);
-      mbar_expect_tx(&sm.b_bar[GRP], kBytes);
-      bulk_g2s(sm.b[GRP], wop + static_cast<size_t>(tile / n_btiles) * kMxOperandFloats, kBytes, &sm.b_bar[GRP]);
-    }
-    mx_split_store(regs, sm.a_hi[GRP], sm.a_lo[GRP], gtid);
-    tc::fence_proxy_async_smem();
-    tc::fence_before_thread_sync();
-    mx_group_barrier<GRP>();
-    tc::fence_after_thread_sync();
-    // refill this register set AFTER the fence: the membar inside fence.proxy.async would otherwise wait for the loads
-    prefetch_tile(regs, it + 2);
-    if (gwarp == 0) {
-      if (tc::elect_one()) {
-        mbar_wait(&sm.b_bar[GRP], it & 1);
-        const uint32_t d_tmem = tmem_base + buf * kMxN;
-        const uint32_t a_s[3] = {tc::smem_addr(sm.a_hi[GRP]), tc::smem_addr(sm.a_lo[GRP]), tc::smem_addr(sm.a_hi[GRP])};
-        const uint32_t b_hi = tc::smem_addr(sm.b[GRP]), b_lo = b_hi + kMxBFloats * sizeof(float);
-        const uint32_t b_s[3] = {b_hi, b_hi, b_lo};
-#pragma unroll
-        for (int pass = 0; pass < 3; ++pass) {
-          const uint64_t da0 = tc::make_smem_desc(a_s[pass], kMxLboA, 128);
-          const uint64_t db0 = tc::make_smem_desc(b_s[pass], kMxLboB, 128);
-#pragma unroll
-          for (int ks = 0; ks < kMxK / 8; ++ks) {
-            const uint64_t da = da0 + ((ks * 2 * kMxLboA) >> 4), db = db0 + ((ks * 2 * kMxLboB) >> 4);
-            if (pass == 0 && ks == 0) tc::mma_tf32_imm<false>(d_tmem, da, db, idesc);
-            else tc::mma_tf32_imm<true>(d_tmem, da, db, idesc);
-          }
-        }
-        tc::mma_commit(&sm.mma_bar[GRP][buf]);
-      }
-      __syncwarp();
-    }
-    if (it >= 1) epilogue(it - 1);
-  };
-  for (int it = 0; it < n_mine; it += 2) {
-    body(it, ring[0]);
-    if (it + 1 < n_mine) body(it + 1, ring[1]);
-  }
-  if (n_mine >= 1) epilogue(n_mine - 1);
-}
-
 __global__ void __launch_bounds__(kMxThreads, 1)
-    mode_mix_tc_kernel(const float4* __restrict__ xm, const float* __restrict__ wop, float4* __restrict__ ym,
-                       unsigned char* __restrict__ ym_img, int batch, int n_btiles, int n_tiles) {
-  extern __shared__ __align__(1024) unsigned char smem_raw[];  // no pointer arithmetic: keeps LDS/STS addressing
+    mode_mix_tc_kernel(const __grid_constant__ CUtensorMap x_map, const float* __restrict__ wop, float4* __restrict__ ym,
+                       unsigned char* __restrict__ ym_img, int batch, int n_btiles) {
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
   MxSmem& sm = *reinterpret_cast<MxSmem*>(smem_raw);
-  if ((smem_u32(smem_raw) & 127u) != 0) __trap();
-  const int tid = threadIdx.x, warp = tc::warp_index_uniform();
-  const int grp = warp >> 3;
+  if ((smem_u32(smem_raw) & 1023u) != 0) __trap();
+  const int tid = threadIdx.x, lane = tid & 31, warp = tc::warp_index_uniform();
+#ifdef FNO_FZ_TRACE
+  long long* const mx_tr = g_mx_trace;
+#endif
+  MX_CTA(0);
+
+  // modes of this CTA: k = first + j * stride; tiles are numbered t = j * n_btiles + bt in processing order
+  const int first = blockIdx.x, stride = gridDim.x;
+  const int n_modes = (first < kModes) ? (kModes - first + stride - 1) / stride : 0;
+  const int n_tiles = n_modes * n_btiles;
+
   if (tid == 0) {
-#pragma unroll
-    for (int i = 0; i < 4; ++i) mbar_init(&sm.mma_bar[i >> 1][i & 1], 1);
-    mbar_init(&sm.b_bar[0], 1);
-    mbar_init(&sm.b_bar[1], 1);
+    for (int i = 0; i < kMxRing; ++i) {
+      mbar_init(&sm.a_full[i], 1);
+      mbar_init(&sm.a_free[i], 1);
+      mbar_init(&sm.d_full[i], 1);
+      mbar_init(&sm.d_free[i], kMxEpiWarps);
+    }
+    for (int i = 0; i < 2; ++i) { mbar_init(&sm.b_full[i], 1); mbar_init(&sm.b_free[i], 1); }
+    mbar_init(&sm.lo_ready, kMxConvWarps);
+    mbar_init(&sm.lo_free, 1);
     fence_mbar_init();
+    // the weights of the first two modes do not depend on the previous kernel of the chain: fetch them now
+    for (int j = 0; j < 2 && j < n_modes; ++j) {
+      mbar_expect_tx(&sm.b_full[j], kMxBBytes);
+      bulk_g2s(sm.b[j], wop + static_cast<size_t>(first + j * stride) * kMxOperandFloats, kMxBBytes, &sm.b_full[j]);
+    }
   }
-  if (warp == 0) tc::tmem_alloc<4 * kMxN>(&sm.tmem_base);
+  if (warp == kMxMmaWarp) tc::tmem_alloc<kMxRing * kMxN>(&sm.tmem_base);
   tc::fence_before_thread_sync();
   __syncthreads();
   tc::fence_after_thread_sync();
-  if (tid == 0) {  // the first tile's weights of both pipelines do not depend on the previous kernel: fetch them now
-    constexpr uint32_t kBytes = kMxOperandFloats * sizeof(float);
-#pragma unroll
-    for (int g = 0; g < 2; ++g) {
-      const int t = blockIdx.x + g * gridDim.x;
-      if (t < n_tiles) {
-        mbar_expect_tx(&sm.b_bar[g], kBytes);
-        bulk_g2s(sm.b[g], wop + static_cast<size_t>(t / n_btiles) * kMxOperandFloats, kBytes, &sm.b_bar[g]);
-      }
-    }
-  }
+  const uint32_t tmem = sm.tmem_base;
+  MX_CTA(1);
   pdl_wait();  // xm comes from the previous kernel of the chain
   pdl_launch_dependents();
-  if (grp == 0) mx_pipeline<0>(sm, xm, wop, ym, ym_img, batch, n_btiles, n_tiles);
-  else mx_pipeline<1>(sm, xm, wop, ym, ym_img, batch, n_btiles, n_tiles);
+
+  // ================================================================ lo-part converters
+  if (warp < kMxConvWarps) {
+    for (int t = 0; t < n_tiles; ++t) {
+      const int s = t % kMxRing;
+      if (tid == 0) MX_T(0, t, 0);
+      mbar_wait(&sm.a_full[s], (t / kMxRing) & 1);
+      if (tid == 0) MX_T(0, t, 1);
+      if (t >= 1) mbar_wait(&sm.lo_free, (t - 1) & 1);   // the lo MMAs of the previous tile have read the buffer
+      if (tid == 0) MX_T(0, t, 2);
+      const float4* src = reinterpret_cast<const float4*>(sm.a[s]);
+      float4* dst = reinterpret_cast<float4*>(sm.a_lo);
+#pragma unroll
+      for (int rep = 0; rep < 8; ++rep) {
+        const int idx = rep * (kMxConvWarps * 32) + tid;
+        const float4 x = src[idx];
+        float4 lo;   // x - trunc_tf32(x) is exact; +0x1000 rounds what the tensor core then truncates
+        lo.x = __uint_as_float(__float_as_uint(x.x - __uint_as_float(__float_as_uint(x.x) & 0xffffe000u)) + 0x1000u);
+        lo.y = __uint_as_float(__float_as_uint(x.y - __uint_as_float(__float_as_uint(x.y) & 0xffffe000u)) + 0x1000u);
+        lo.z = __uint_as_float(__float_as_uint(x.z - __uint_as_float(__float_as_uint(x.z) & 0xffffe000u)) + 0x1000u);
+        lo.w = __uint_as_float(__float_as_uint(x.w - __uint_as_float(__float_as_uint(x.w) & 0xffffe000u)) + 0x1000u);
+        dst[idx] = lo;
+      }
+      tc::fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&sm.lo_ready);
+      if (tid == 0) MX_T(0, t, 3);
+    }
+  }
+  // ================================================================ epilogue
+  // warps w and w+4 share TMEM lane quadrant w & 3 (rows 32 (w&3) .. +31 of the tile) and take the 32-float column halves
+  else if (warp < kMxConvWarps + kMxEpiWarps) {
+    const int quad = warp & 3, half = (warp >> 2) & 1;
+    for (int t = 0; t < n_tiles; ++t) {
+      const int s = t % kMxRing;
+      const int k = first + (t / n_btiles) * stride, b = (t % n_btiles) * kMxM + quad * 32 + lane;
+      if (warp == kMxConvWarps && lane == 0) MX_T(1, t, 0);
+      mbar_wait(&sm.d_full[s], (t / kMxRing) & 1);
+      tc::fence_after_thread_sync();
+      if (warp == kMxConvWarps && lane == 0) MX_T(1, t, 1);
+      float v[32];
+      tc::tmem_ld32(tmem + (static_cast<uint32_t>(quad * 32) << 16) + s * kMxN + half * 32, v);
+      tc::fence_before_thread_sync();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&sm.d_free[s]);
+      if (b < batch && ym_img == nullptr) {
+        float4* dst = ym + (static_cast<size_t>(k) * batch + b) * (kC / 2) + half * 8;
+#pragma unroll
+        for (int c = 0; c < 8; ++c) dst[c] = make_float4(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
+      } else if (b < batch) {
+        // Operand image of block_fused_kernel's GEMM1 (fno_block_fused.cu): per sample [hi|lo][ky/4][ky%4][48 rows][32 o]
+        // fp32, row = 24 (kxi & 1) + 2 (kxi >> 1) + (re|im), 32-byte chunks XOR-swizzled with (row & 3); tf32 hi / lo
+        // split here so the consumer is pure bulk copy + MMA.  This thread holds o = 16 half .. 16 half + 15, (re, im).
+        const int kxi = k / kM2, ky = k % kM2;
+        unsigned char* img = ym_img + static_cast<size_t>(b) * 147456 + (ky >> 2) * 24576 + (ky & 3) * 6144;
+#pragma unroll
+        for (int ri = 0; ri < 2; ++ri) {
+          const int row = 24 * (kxi & 1) + 2 * (kxi >> 1) + ri;
+#pragma unroll
+          for (int c = 0; c < 2; ++c) {
+            float hi[8], lo[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) tc::split_tf32(v[2 * (8 * c + j) + ri], hi[j], lo[j]);
+            unsigned char* dst = img + row * 128 + (((2 * half + c) ^ (row & 3)) << 5);
+            mx_store32(dst, hi);            // one 32-byte chunk = one full sector per store instruction
+            mx_store32(dst + 73728, lo);
+          }
+        }
+      }
+      if (warp == kMxConvWarps && lane == 0) MX_T(1, t, 2);
+    }
+  }
+  // ================================================================ producer
+  else if (warp == kMxProdWarp) {
+    if (lane == 0) {
+      int t = 0;
+      for (int j = 0; j < n_modes; ++j) {
+        const int k = first + j * stride;
+        if (j >= 2) {   // modes 0 and 1 were requested in the prologue
+          mbar_wait(&sm.b_free[j & 1], ((j >> 1) - 1) & 1);
+          mbar_expect_tx(&sm.b_full[j & 1], kMxBBytes);
+          bulk_g2s(sm.b[j & 1], wop + static_cast<size_t>(k) * kMxOperandFloats, kMxBBytes, &sm.b_full[j & 1]);
+        }
+        for (int bt = 0; bt < n_btiles; ++bt, ++t) {
+          const int s = t % kMxRing;
+          if (t >= kMxRing) mbar_wait(&sm.a_free[s], ((t / kMxRing) - 1) & 1);
+          MX_T(2, t, 0);
+          mbar_expect_tx(&sm.a_full[s], kMxABytes);
+          const int row0 = k * batch + bt * kMxM;   // rows past this mode's samples are never stored by the epilogue
+          fz_tma_load_2d(sm.a[s], &x_map, 0, row0, &sm.a_full[s]);
+          fz_tma_load_2d(sm.a[s] + kMxABytes / 2, &x_map, 32, row0, &sm.a_full[s]);
+        }
+      }
+    }
+    __syncwarp();
+  }
+  // ================================================================ MMA issue
+  else if (warp == kMxMmaWarp) {
+    if (tc::elect_one()) {
+      constexpr uint32_t idesc = tc::make_idesc_tf32(kMxM, kMxN);
+      const uint32_t lo_s = tc::smem_addr(sm.a_lo);
+      int t = 0;
+#pragma unroll 1
+      for (int j = 0; j < n_modes; ++j) {
+        mbar_wait(&sm.b_full[j & 1], (j >> 1) & 1);
+        const uint32_t b_hi = tc::smem_addr(sm.b[j & 1]), b_lo = b_hi + kMxBFloats * 4;
+#pragma unroll 1
+        for (int bt = 0; bt < n_btiles; ++bt, ++t) {
+          const int s = t % kMxRing;
+          MX_T(3, t, 0);
+          mbar_wait(&sm.a_full[s], (t / kMxRing) & 1);
+          if (t >= kMxRing) mbar_wait(&sm.d_free[s], ((t / kMxRing) - 1) & 1);
+          tc::fence_after_thread_sync();
+          MX_T(3, t, 1);
+          const uint32_t d = tmem + s * kMxN, a_s = tc::smem_addr(sm.a[s]);
+#pragma unroll
+          for (int pass = 0; pass < 3; ++pass) {
+            if (pass == 2) {
+              MX_T(3, t, 2);
+              mbar_wait(&sm.lo_ready, t & 1);
+              tc::fence_after_thread_sync();
+              MX_T(3, t, 3);
+            }
+            const uint32_t pa = (pass == 2) ? lo_s : a_s, pb = (pass == 1) ? b_lo : b_hi;
+#pragma unroll
+            for (int ks = 0; ks < kMxK / 8; ++ks)   // K = 8 per MMA: 32 bytes inside the 128-byte swizzle row of a K half
+              fz_mma_tf32_ss(d, fz_desc_sw128(pa + (ks >> 2) * (kMxABytes / 2) + (ks & 3) * 32, 0, 1024),
+                             tc::make_smem_desc(pb + ks * 2 * kMxLboB, kMxLboB, 128), idesc, (pass | ks) ? 1u : 0u);
+          }
+          tc::mma_commit(&sm.a_free[s]);
+          tc::mma_commit(&sm.lo_free);
+          tc::mma_commit(&sm.d_full[s]);
+          if (bt == n_btiles - 1) tc::mma_commit(&sm.b_free[j & 1]);
+          MX_T(3, t, 4);
+        }
+      }
+    }
+    __syncwarp();
+  }
+
   tc::fence_before_thread_sync();
   __syncthreads();
-  if (warp == 0) tc::tmem_dealloc<4 * kMxN>(sm.tmem_base);
+  MX_CTA(2);
+  if (warp == kMxMmaWarp) tc::tmem_dealloc<kMxRing * kMxN>(tmem);
+}
+
+#ifdef FNO_FZ_TRACE
+extern "C" int fno_debug_mix_trace(void* p) {
+  long long* q = static_cast<long long*>(p);
+  return cudaMemcpyToSymbol(g_mx_trace, &q, sizeof(q)) == cudaSuccess ? 0 : 2;
+}
+#endif
+
+// tensor map of the mode-major spectrum as rows of 64 floats: [288 * batch rows][64], box {32 floats, 128 rows}
+static cudaError_t mx_make_map(const void* xm, int batch, CUtensorMap* out) {
+  static FzEncodeFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q);
+    if (e != cudaSuccess) return e;
+    if (!p) return cudaErrorNotSupported;
+    fn = reinterpret_cast<FzEncodeFn>(p);
+  }
+  const cuuint64_t gdim[2] = {static_cast<cuuint64_t>(kMxK), static_cast<cuuint64_t>(kModes) * batch};
+  const cuuint64_t gstride[1] = {static_cast<cuuint64_t>(kMxK) * 4};
+  const cuuint32_t box[2] = {32, static_cast<cuuint32_t>(kMxM)}, estr[2] = {1, 1};
+  const CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(xm), gdim, gstride, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? cudaSuccess : cudaErrorInvalidValue;
 }
 
 // ym_img != nullptr: write the per-sample GEMM1 operand image (see the epilogue) instead of the mode-major ym.
@@ -255,12 +308,14 @@ cudaError_t launch_mode_mix(const void* xm, const void* wop, void* ym, void* ym_
   int n_sm = 0;
   cudaError_t e0 = per_device_setup(kern, smem, pd, &n_sm);
   if (e0 != cudaSuccess) return e0;
+  if (reinterpret_cast<uintptr_t>(xm) & 15) return cudaErrorMisalignedAddress;
+  CUtensorMap map;
+  e0 = mx_make_map(xm, batch, &map);
+  if (e0 != cudaSuccess) return e0;
   const int n_btiles = (batch + kMxM - 1) / kMxM;
-  const int n_tiles = kModes * n_btiles;
-  const int grid = n_tiles < 2 * n_sm ? (n_tiles + 1) / 2 : n_sm;
-  return launch_chained(kern, dim3(grid), dim3(kMxThreads), smem, stream, static_cast<const float4*>(xm),
-                        static_cast<const float*>(wop), static_cast<float4*>(ym), static_cast<unsigned char*>(ym_img), batch,
-                        n_btiles, n_tiles);
+  const int grid = kModes < n_sm ? kModes : n_sm;
+  return launch_chained(kern, dim3(grid), dim3(kMxThreads), smem, stream, map, static_cast<const float*>(wop),
+                        static_cast<float4*>(ym), static_cast<unsigned char*>(ym_img), batch, n_btiles);
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -35,8 +35,22 @@ for it in range(3):
         assert lib.fno_debug_fused_trace(trace.data_ptr()) == 0
     _lib.check(lib.fno_block_fused(img.data_ptr(), x.data_ptr(), w0t.data_ptr(), bias.data_ptr(), out.data_ptr(), batch, st), "fused")
     torch.cuda.synchronize()
-ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(10)]
 assert lib.fno_debug_fused_trace(None) == 0
+def timed(label):
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(10)]
+    for a, z in ev:
+        a.record()
+        _lib.check(lib.fno_block_fused(img.data_ptr(), x.data_ptr(), w0t.data_ptr(), bias.data_ptr(), out.data_ptr(), batch, st), "fused")
+        z.record()
+    torch.cuda.synchronize()
+    print(label, "median us", np.median([a.elapsed_time(z) * 1e3 for a, z in ev]).round(1))
+lib.fno_debug_fused_knock.argtypes = [C.c_int]
+for bits, label in ((0, "full kernel"), (1, "no conv MMAs"), (2, "no E MMAs"), (4, "no GEMM1 MMAs"), (8, "no converter stores"), (16, "no GELU"), (32, "no output stores"),
+                    (3, "no tile MMAs"), (7, "no MMAs"), (48, "no GELU, no stores"), (15, "no MMAs, no conv stores"), (55, "no MMAs, GELU, stores"), (63, "skeleton only")):
+    assert lib.fno_debug_fused_knock(bits) == 0
+    timed("knock-out %2d %-26s" % (bits, label))
+assert lib.fno_debug_fused_knock(0) == 0
+ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(10)]
 for a, z in ev:
     a.record()
     _lib.check(lib.fno_block_fused(img.data_ptr(), x.data_ptr(), w0t.data_ptr(), bias.data_ptr(), out.data_ptr(), batch, st), "fused")
