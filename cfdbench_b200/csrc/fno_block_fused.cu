@@ -165,10 +165,27 @@ __global__ void __launch_bounds__(kFzThreads, 1)
     bulk_g2s(sm.f, ftab, kFzFBytes, &sm.f_bar);   // twiddle operand, already in its K-major tf32 hi|lo layout
   }
   if (warp == kFzMmaWarp) tc::tmem_alloc<512>(&sm.tmem_base);
+  // The constant E operand goes to tensor memory below; its 48 values per thread are requested NOW, so that their L2
+  // round trip overlaps the TMEM allocation and the W0 conversion (loaded 16 at a time after the barrier, the three
+  // dependent round trips made this prologue 6,400 cycles per CTA).
+  const bool loads_e = warp >= kFzConvWarps && warp < kFzConvWarps + kFzEpiWarps;
+  float e_val[48];
+  if (loads_e) {
+    const int m = (warp & 3) * 32 + lane, cbase = ((warp - kFzConvWarps) >> 2) * 48;
+#pragma unroll
+    for (int j = 0; j < 48; ++j) e_val[j] = __ldg(etab + (cbase + j) * 128 + m);
+  }
   // W0 -> three bf16 pieces, B operand [n = o][k = i], K-major, no swizzle (8 x 16-byte core matrices)
-  for (int e = tid; e < kC * kC; e += kFzThreads) {
+  float w_val[2];
+#pragma unroll
+  for (int it = 0; it < 2; ++it) w_val[it] = (tid + it * kFzThreads < kC * kC) ? w0t[tid + it * kFzThreads] : 0.f;
+  static_assert(2 * kFzThreads >= kC * kC, "two W0 elements per thread");
+#pragma unroll
+  for (int it = 0; it < 2; ++it) {
+    const int e = tid + it * kFzThreads;
+    if (e >= kC * kC) break;
     const int i = e / kC, o = e % kC;   // w0t[i][o] = W0[o][i]
-    const float wv = w0t[e];
+    const float wv = w_val[it];
     const __nv_bfloat16 p0 = __float2bfloat16_rn(wv);
     const float r1 = wv - __bfloat162float(p0);
     const __nv_bfloat16 p1 = __float2bfloat16_rn(r1);
@@ -184,18 +201,14 @@ __global__ void __launch_bounds__(kFzThreads, 1)
   __syncthreads();
   tc::fence_after_thread_sync();
   const uint32_t tmem = sm.tmem_base;
-  if (warp >= kFzConvWarps && warp < kFzConvWarps + kFzEpiWarps) {
+  if (loads_e) {
     // constant E operand -> tensor memory (row m in lane m).  The table is stored column-major (etab[c][m]) so that a warp
     // reads 128 contiguous bytes per column; with the row-major table every load touched 32 lines and this prologue cost
     // 17,000 cycles per CTA (a quarter of the kernel, FNO_FZ_TRACE).  Two warps per lane quadrant, 48 columns each.
-    const int m = (warp & 3) * 32 + lane, cbase = ((warp - kFzConvWarps) >> 2) * 48;
+    const int cbase = ((warp - kFzConvWarps) >> 2) * 48;
 #pragma unroll
-    for (int c0 = 0; c0 < 48; c0 += 16) {
-      float v[16];
-#pragma unroll
-      for (int j = 0; j < 16; ++j) v[j] = __ldg(etab + (cbase + c0 + j) * 128 + m);
-      tc::tmem_st16(tmem + kFzColE + cbase + c0 + (static_cast<uint32_t>((warp & 3) * 32) << 16), v);
-    }
+    for (int c0 = 0; c0 < 48; c0 += 16)
+      tc::tmem_st16(tmem + kFzColE + cbase + c0 + (static_cast<uint32_t>((warp & 3) * 32) << 16), e_val + c0);
     tc::tmem_wait_st();
   }
   mbar_wait(&sm.f_bar, 0);

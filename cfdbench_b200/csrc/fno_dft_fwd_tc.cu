@@ -163,13 +163,12 @@ __global__ void __launch_bounds__(kTdThreads, 1)
     // in accumulator rows nobody reads).  The table is stored column-major in LANE order, so that a warp reads 128
     // contiguous bytes per column; 4 warps per lane quadrant, 32 columns each.
     const int m = (warp & 3) * 32 + lane, cbase = (warp >> 2) * 32;
+    float v[32];
 #pragma unroll
-    for (int c0 = 0; c0 < 32; c0 += 16) {
-      float v[16];
+    for (int j = 0; j < 32; ++j) v[j] = __ldg(a2_tab + (cbase + j) * kTdA2Rows + m);   // one L2 round trip, not two
 #pragma unroll
-      for (int j = 0; j < 16; ++j) v[j] = __ldg(a2_tab + (cbase + c0 + j) * kTdA2Rows + m);
-      tc::tmem_st16(tmem + kTdColA2 + cbase + c0 + (static_cast<uint32_t>((warp & 3) * 32) << 16), v);
-    }
+    for (int c0 = 0; c0 < 32; c0 += 16)
+      tc::tmem_st16(tmem + kTdColA2 + cbase + c0 + (static_cast<uint32_t>((warp & 3) * 32) << 16), v + c0);
     tc::tmem_wait_st();
   }
   tc::fence_before_thread_sync();

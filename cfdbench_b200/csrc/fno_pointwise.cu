@@ -36,31 +36,37 @@ __global__ void __launch_bounds__(kLiftThreads)
     for (int q = 0; q < 5; ++q) sw[tid][q] = w[tid * nin + q];
   }
   __syncthreads();
-  const int pix = (blockIdx.x * kLiftThreads + tid) * 4;  // 4 consecutive pixels of one row
+  // 16-byte stores for both storage types: 4 fp32 or 8 bf16 consecutive pixels of one row per thread and channel
+  constexpr int kPx = 16 / sizeof(TAct);
+  const int pix = (blockIdx.x * kLiftThreads + tid) * kPx;
   const int h = pix >> 6, w0 = pix & 63;
-  const float4 u = *reinterpret_cast<const float4*>(inputs + (static_cast<size_t>(b) * 2 + 0) * kHW + pix);
-  const float4 v = *reinterpret_cast<const float4*>(inputs + (static_cast<size_t>(b) * 2 + 1) * kHW + pix);
-  const float4 m = *reinterpret_cast<const float4*>(mask + static_cast<size_t>(b) * kHW + pix);
+  float u[kPx], v[kPx], m[kPx], yw[kPx];
+#pragma unroll
+  for (int j = 0; j < kPx; j += 4) {
+    *reinterpret_cast<float4*>(u + j) = *reinterpret_cast<const float4*>(inputs + (static_cast<size_t>(b) * 2 + 0) * kHW + pix + j);
+    *reinterpret_cast<float4*>(v + j) = *reinterpret_cast<const float4*>(inputs + (static_cast<size_t>(b) * 2 + 1) * kHW + pix + j);
+    *reinterpret_cast<float4*>(m + j) = *reinterpret_cast<const float4*>(mask + static_cast<size_t>(b) * kHW + pix + j);
+    *reinterpret_cast<float4*>(yw + j) = *reinterpret_cast<const float4*>(gy + w0 + j);
+  }
   const float xh = gx[h];
-  const float4 yw = *reinterpret_cast<const float4*>(gy + w0);
   TAct* dst = out + static_cast<size_t>(b) * kC * kHW + pix;
 #pragma unroll 4
   for (int c = 0; c < kC; ++c) {
     const float wu = sw[c][0], wv = sw[c][1], wm = sw[c][2], wx = sw[c][3], wy = sw[c][4];
     const float base = fmaf(wx, xh, scb[c]);
-    float4 r;
-    r.x = fmaf(wu, u.x, fmaf(wv, v.x, fmaf(wm, m.x, fmaf(wy, yw.x, base))));
-    r.y = fmaf(wu, u.y, fmaf(wv, v.y, fmaf(wm, m.y, fmaf(wy, yw.y, base))));
-    r.z = fmaf(wu, u.z, fmaf(wv, v.z, fmaf(wm, m.z, fmaf(wy, yw.z, base))));
-    r.w = fmaf(wu, u.w, fmaf(wv, v.w, fmaf(wm, m.w, fmaf(wy, yw.w, base))));
+    float r[kPx];
+#pragma unroll
+    for (int j = 0; j < kPx; ++j) r[j] = fmaf(wu, u[j], fmaf(wv, v[j], fmaf(wm, m[j], fmaf(wy, yw[j], base))));
     if constexpr (sizeof(TAct) == 4) {
-      *reinterpret_cast<float4*>(dst + static_cast<size_t>(c) * kHW) = r;
+      *reinterpret_cast<float4*>(dst + static_cast<size_t>(c) * kHW) = make_float4(r[0], r[1], r[2], r[3]);
     } else {
-      __nv_bfloat162 lo = __floats2bfloat162_rn(r.x, r.y), hi = __floats2bfloat162_rn(r.z, r.w);
-      uint2 pk;
-      pk.x = *reinterpret_cast<uint32_t*>(&lo);
-      pk.y = *reinterpret_cast<uint32_t*>(&hi);
-      *reinterpret_cast<uint2*>(dst + static_cast<size_t>(c) * kHW) = pk;
+      uint4 pk;
+      __nv_bfloat162 t;
+      t = __floats2bfloat162_rn(r[0], r[1]); pk.x = *reinterpret_cast<uint32_t*>(&t);
+      t = __floats2bfloat162_rn(r[2], r[3]); pk.y = *reinterpret_cast<uint32_t*>(&t);
+      t = __floats2bfloat162_rn(r[4], r[5]); pk.z = *reinterpret_cast<uint32_t*>(&t);
+      t = __floats2bfloat162_rn(r[6], r[7]); pk.w = *reinterpret_cast<uint32_t*>(&t);
+      *reinterpret_cast<uint4*>(dst + static_cast<size_t>(c) * kHW) = pk;
     }
   }
 }
@@ -70,7 +76,7 @@ cudaError_t launch_lift(const float* inputs, const float* mask, const float* par
                         const float* bias, const float* gx, const float* gy, void* out, int batch, int p,
                         cudaStream_t stream) {
   if (p < 0 || p > kMaxCaseParams) return cudaErrorInvalidValue;
-  dim3 grid(kHW / (kLiftThreads * 4), batch);
+  dim3 grid(kHW / (kLiftThreads * (16 / static_cast<int>(sizeof(TAct)))), batch);
   return launch_chained(lift_kernel<TAct>, grid, dim3(kLiftThreads), 0, stream, inputs, mask, params, w, bias, gx, gy,
                         static_cast<TAct*>(out), p);
 }
