@@ -90,6 +90,10 @@ struct FzSmem {
   // super-tiles, and with an odd ring size a role would otherwise see only every other phase of a slot's barrier, which
   // the one-bit phase parity cannot express (a wait could match the completion of three super-tiles earlier).
   alignas(8) uint64_t ready[2 * kFzR], slot_free[2 * kFzR], d2_full[2 * kFzR];
+  // pace[s]: the same completion event once more, consumed by the GEMM1 thread: it spreads the 54 MMAs of the NEXT unit's
+  // inverse-kx GEMM over the super-tiles of the current unit (one stage per super-tile) instead of queueing them in one
+  // ~3,200-cycle burst in front of the tile MMAs the three-slot ring is waiting for
+  uint64_t pace[2 * kFzR];
   uint64_t y_full[kFzNY], y_empty[kFzNY];
   uint64_t d1_full, d1_free, f_bar;
   uint32_t tmem_base;
@@ -155,6 +159,7 @@ __global__ void __launch_bounds__(kFzThreads, 1)
       mbar_init(&sm.ready[i], kFzReadyCount);
       mbar_init(&sm.slot_free[i], 1);
       mbar_init(&sm.d2_full[i], 1);
+      mbar_init(&sm.pace[i], 1);
     }
     for (int i = 0; i < kFzNY; ++i) { mbar_init(&sm.y_full[i], 1); mbar_init(&sm.y_empty[i], 1); }
     mbar_init(&sm.d1_full, 1);
@@ -366,6 +371,7 @@ __global__ void __launch_bounds__(kFzThreads, 1)
         }
         tc::mma_commit(&sm.slot_free[fz_bar(S)]);
         tc::mma_commit(&sm.d2_full[fz_bar(S)]);
+        tc::mma_commit(&sm.pace[fz_bar(S)]);
         FZ_T(2, S, 5);
       }
     }
@@ -376,6 +382,7 @@ __global__ void __launch_bounds__(kFzThreads, 1)
   else if (warp == kFzG1Warp) {
     if (tc::elect_one()) {
       const uint32_t f_hi = tc::smem_addr(sm.f), f_lo = f_hi + kFzFBytes / 2;
+      int pace_next = 0;   // first super-tile whose completion this thread has not consumed yet
       constexpr uint32_t idesc_g64 = tc::make_idesc_tf32(128, 64) | kAMajorMN;
       constexpr uint32_t idesc_g32 = tc::make_idesc_tf32(128, 32) | kAMajorMN;
 #pragma unroll 1
@@ -391,6 +398,14 @@ __global__ void __launch_bounds__(kFzThreads, 1)
         }
 #pragma unroll 1
         for (int st = 0; st < 6; ++st) {
+          // pacing: the stages of unit k >= 1 go behind super-tiles 2..5 of unit k-1 -- after the converters have released
+          // D1 (d1_free, around super-tile 1) and before they want the new D1 (three super-tiles ahead of the MMAs).  This
+          // thread observes EVERY phase of the pace barriers, in order, so the one-bit parity stays unambiguous.
+          if (k >= 1) {
+            const int s_hi = (k - 1) * kFzSPU + 2 + (2 * st) / 3;   // super-tiles 2,2,3,4,4,5 of the previous unit
+            for (; pace_next <= s_hi && pace_next < n_super_all; ++pace_next)
+              mbar_wait(&sm.pace[fz_bar(pace_next)], fz_phase(pace_next));
+          }
           const int c = k * 6 + st, slot = c % kFzNY;
           const int mt = st >> 1, par = st & 1;
           FZ_T(3, k * 8 + st, 0);
