@@ -18,8 +18,11 @@
 //     boxes, 128-byte swizzle) into a 4-slot ring as a K-major operand.  At B = 256 the ring holds ALL the tiles of a CTA,
 //     so every load of the kernel is in flight from the first microsecond;
 //   * the tensor core truncates what it reads to tf32, so the raw tile IS the hi operand; warps 0-7 compute the lo part
-//     (x - trunc(x), exact, then rounded) element by element at the SAME swizzled offsets into a second buffer;
-//   * warp 17 -- MMA issue: A_raw x B_hi, A_raw x B_lo (16 MMAs, need only the TMA data) then A_lo x B_hi (8);
+//     (x - trunc(x), exact, then rounded) as soon as a tile lands and put it into TENSOR MEMORY (thread = sample row =
+//     TMEM lane; one 64-column block per ring slot), where it is the A operand of the third pass.  (A first version kept
+//     one lo buffer in shared memory, refilled per tile: the refill's LDS/STS then ran concurrently with the previous
+//     tile's 64 KB of global stores and took ~4,000 cycles instead of ~300, serialising the tiles -- tools/trace_mix.py.)
+//   * warp 17 -- MMA issue: A_raw x B_hi, A_raw x B_lo (16 MMAs, need only the TMA data) then A_lo x B_hi (8, A in TMEM);
 //     4 accumulators of 64 columns, so the epilogue of a tile never holds up the next tile's MMAs;
 //   * warps 8-15 -- epilogue: mode-major ym rows (fp32 path / backward) or the per-sample operand image of
 //     block_fused_kernel's GEMM1 (tf32 hi/lo split here, 256-bit stores).
@@ -68,13 +71,13 @@ __device__ long long* g_mx_trace = nullptr;
 
 struct MxSmem {
   alignas(1024) unsigned char a[kMxRing][kMxABytes];   // raw fp32 tiles (TMA, 128B swizzle): the hi operand
-  alignas(1024) unsigned char a_lo[kMxABytes];         // lo operand of the tile being multiplied
   alignas(1024) float b[2][kMxOperandFloats];          // [mode parity] hi | lo images
-  alignas(8) uint64_t a_full[kMxRing], a_free[kMxRing], d_full[kMxRing], d_free[kMxRing];
+  alignas(8) uint64_t a_full[kMxRing], a_free[kMxRing], d_full[kMxRing], d_free[kMxRing], lo_ready[kMxRing];
   uint64_t b_full[2], b_free[2];
-  uint64_t lo_ready, lo_free;
   uint32_t tmem_base;
 };
+constexpr uint32_t kMxColD = 0, kMxColLo = kMxRing * kMxN;   // tensor memory: 4 accumulators, then 4 lo operands
+constexpr int kMxTmemCols = 2 * kMxRing * kMxN;              // 512
 
 // 256-bit global store (sm_100: st.global.v8): the image epilogue writes 32-byte chunks of 32 different samples per warp
 // instruction, so the instruction count -- not the bytes -- is what the LSU queue sees (lg_throttle 5.0 per issue with
@@ -108,10 +111,9 @@ __global__ void __launch_bounds__(kMxThreads, 1)
       mbar_init(&sm.a_free[i], 1);
       mbar_init(&sm.d_full[i], 1);
       mbar_init(&sm.d_free[i], kMxEpiWarps);
+      mbar_init(&sm.lo_ready[i], kMxConvWarps);
     }
     for (int i = 0; i < 2; ++i) { mbar_init(&sm.b_full[i], 1); mbar_init(&sm.b_free[i], 1); }
-    mbar_init(&sm.lo_ready, kMxConvWarps);
-    mbar_init(&sm.lo_free, 1);
     fence_mbar_init();
     // the weights of the first two modes do not depend on the previous kernel of the chain: fetch them now
     for (int j = 0; j < 2 && j < n_modes; ++j) {
@@ -119,7 +121,7 @@ __global__ void __launch_bounds__(kMxThreads, 1)
       bulk_g2s(sm.b[j], wop + static_cast<size_t>(first + j * stride) * kMxOperandFloats, kMxBBytes, &sm.b_full[j]);
     }
   }
-  if (warp == kMxMmaWarp) tc::tmem_alloc<kMxRing * kMxN>(&sm.tmem_base);
+  if (warp == kMxMmaWarp) tc::tmem_alloc<kMxTmemCols>(&sm.tmem_base);
   tc::fence_before_thread_sync();
   __syncthreads();
   tc::fence_after_thread_sync();
@@ -130,29 +132,34 @@ __global__ void __launch_bounds__(kMxThreads, 1)
 
   // ================================================================ lo-part converters
   if (warp < kMxConvWarps) {
+    // thread = sample row m = 32 quad + lane (its TMEM lane) and one K half (32 floats = one swizzled 128-byte segment)
+    const int quad = warp & 3, kh = warp >> 2, m = quad * 32 + lane;
+    const uint32_t t_dst0 = tmem + kMxColLo + kh * 32 + (static_cast<uint32_t>(quad * 32) << 16);
     for (int t = 0; t < n_tiles; ++t) {
       const int s = t % kMxRing;
       if (tid == 0) MX_T(0, t, 0);
       mbar_wait(&sm.a_full[s], (t / kMxRing) & 1);
       if (tid == 0) MX_T(0, t, 1);
-      if (t >= 1) mbar_wait(&sm.lo_free, (t - 1) & 1);   // the lo MMAs of the previous tile have read the buffer
+      // the lo block of this slot was last read by the MMAs of tile t - kMxRing, whose completion released the slot to the
+      // producer (a_free) before this tile could land: no separate barrier
       if (tid == 0) MX_T(0, t, 2);
-      const float4* src = reinterpret_cast<const float4*>(sm.a[s]);
-      float4* dst = reinterpret_cast<float4*>(sm.a_lo);
+      const unsigned char* row = sm.a[s] + kh * (kMxABytes / 2) + m * 128;
+      float lo[32];
 #pragma unroll
-      for (int rep = 0; rep < 8; ++rep) {
-        const int idx = rep * (kMxConvWarps * 32) + tid;
-        const float4 x = src[idx];
-        float4 lo;   // x - trunc_tf32(x) is exact; +0x1000 rounds what the tensor core then truncates
-        lo.x = __uint_as_float(__float_as_uint(x.x - __uint_as_float(__float_as_uint(x.x) & 0xffffe000u)) + 0x1000u);
-        lo.y = __uint_as_float(__float_as_uint(x.y - __uint_as_float(__float_as_uint(x.y) & 0xffffe000u)) + 0x1000u);
-        lo.z = __uint_as_float(__float_as_uint(x.z - __uint_as_float(__float_as_uint(x.z) & 0xffffe000u)) + 0x1000u);
-        lo.w = __uint_as_float(__float_as_uint(x.w - __uint_as_float(__float_as_uint(x.w) & 0xffffe000u)) + 0x1000u);
-        dst[idx] = lo;
+      for (int c = 0; c < 8; ++c) {   // logical 16-byte chunk c of the row sits at position c ^ (m & 7)
+        const float4 x = *reinterpret_cast<const float4*>(row + ((c ^ (m & 7)) << 4));
+        // x - trunc_tf32(x) is exact; +0x1000 rounds what the tensor core then truncates
+        lo[4 * c + 0] = __uint_as_float(__float_as_uint(x.x - __uint_as_float(__float_as_uint(x.x) & 0xffffe000u)) + 0x1000u);
+        lo[4 * c + 1] = __uint_as_float(__float_as_uint(x.y - __uint_as_float(__float_as_uint(x.y) & 0xffffe000u)) + 0x1000u);
+        lo[4 * c + 2] = __uint_as_float(__float_as_uint(x.z - __uint_as_float(__float_as_uint(x.z) & 0xffffe000u)) + 0x1000u);
+        lo[4 * c + 3] = __uint_as_float(__float_as_uint(x.w - __uint_as_float(__float_as_uint(x.w) & 0xffffe000u)) + 0x1000u);
       }
-      tc::fence_proxy_async_smem();
+      tc::tmem_st16(t_dst0 + s * kMxN, lo);
+      tc::tmem_st16(t_dst0 + s * kMxN + 16, lo + 16);
+      tc::tmem_wait_st();
+      tc::fence_before_thread_sync();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&sm.lo_ready);
+      if (lane == 0) mbar_arrive(&sm.lo_ready[s]);
       if (tid == 0) MX_T(0, t, 3);
     }
   }
@@ -168,7 +175,7 @@ __global__ void __launch_bounds__(kMxThreads, 1)
       tc::fence_after_thread_sync();
       if (warp == kMxConvWarps && lane == 0) MX_T(1, t, 1);
       float v[32];
-      tc::tmem_ld32(tmem + (static_cast<uint32_t>(quad * 32) << 16) + s * kMxN + half * 32, v);
+      tc::tmem_ld32(tmem + kMxColD + (static_cast<uint32_t>(quad * 32) << 16) + s * kMxN + half * 32, v);
       tc::fence_before_thread_sync();
       __syncwarp();
       if (lane == 0) mbar_arrive(&sm.d_free[s]);
@@ -227,7 +234,6 @@ __global__ void __launch_bounds__(kMxThreads, 1)
   else if (warp == kMxMmaWarp) {
     if (tc::elect_one()) {
       constexpr uint32_t idesc = tc::make_idesc_tf32(kMxM, kMxN);
-      const uint32_t lo_s = tc::smem_addr(sm.a_lo);
       int t = 0;
 #pragma unroll 1
       for (int j = 0; j < n_modes; ++j) {
@@ -241,23 +247,23 @@ __global__ void __launch_bounds__(kMxThreads, 1)
           if (t >= kMxRing) mbar_wait(&sm.d_free[s], ((t / kMxRing) - 1) & 1);
           tc::fence_after_thread_sync();
           MX_T(3, t, 1);
-          const uint32_t d = tmem + s * kMxN, a_s = tc::smem_addr(sm.a[s]);
+          const uint32_t d = tmem + kMxColD + s * kMxN, a_s = tc::smem_addr(sm.a[s]);
 #pragma unroll
-          for (int pass = 0; pass < 3; ++pass) {
-            if (pass == 2) {
-              MX_T(3, t, 2);
-              mbar_wait(&sm.lo_ready, t & 1);
-              tc::fence_after_thread_sync();
-              MX_T(3, t, 3);
-            }
-            const uint32_t pa = (pass == 2) ? lo_s : a_s, pb = (pass == 1) ? b_lo : b_hi;
+          for (int pass = 0; pass < 2; ++pass) {   // A_raw x B_hi, A_raw x B_lo
+            const uint32_t pb = pass ? b_lo : b_hi;
 #pragma unroll
             for (int ks = 0; ks < kMxK / 8; ++ks)   // K = 8 per MMA: 32 bytes inside the 128-byte swizzle row of a K half
-              fz_mma_tf32_ss(d, fz_desc_sw128(pa + (ks >> 2) * (kMxABytes / 2) + (ks & 3) * 32, 0, 1024),
+              fz_mma_tf32_ss(d, fz_desc_sw128(a_s + (ks >> 2) * (kMxABytes / 2) + (ks & 3) * 32, 0, 1024),
                              tc::make_smem_desc(pb + ks * 2 * kMxLboB, kMxLboB, 128), idesc, (pass | ks) ? 1u : 0u);
           }
+          MX_T(3, t, 2);
+          mbar_wait(&sm.lo_ready[s], (t / kMxRing) & 1);
+          tc::fence_after_thread_sync();
+          MX_T(3, t, 3);
+#pragma unroll
+          for (int ks = 0; ks < kMxK / 8; ++ks)   // A_lo (tensor memory) x B_hi
+            fz_mma_tf32_ts(d, tmem + kMxColLo + s * kMxN + ks * 8, tc::make_smem_desc(b_hi + ks * 2 * kMxLboB, kMxLboB, 128), idesc, 1u);
           tc::mma_commit(&sm.a_free[s]);
-          tc::mma_commit(&sm.lo_free);
           tc::mma_commit(&sm.d_full[s]);
           if (bt == n_btiles - 1) tc::mma_commit(&sm.b_free[j & 1]);
           MX_T(3, t, 4);
@@ -270,7 +276,7 @@ __global__ void __launch_bounds__(kMxThreads, 1)
   tc::fence_before_thread_sync();
   __syncthreads();
   MX_CTA(2);
-  if (warp == kMxMmaWarp) tc::tmem_dealloc<kMxRing * kMxN>(tmem);
+  if (warp == kMxMmaWarp) tc::tmem_dealloc<kMxTmemCols>(tmem);
 }
 
 #ifdef FNO_FZ_TRACE
