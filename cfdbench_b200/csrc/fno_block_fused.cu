@@ -22,9 +22,10 @@
 //   epilogue   8 warps: TMEM -> registers -> exact-erf GELU -> bf16 -> global.
 // Warp roles (768 threads): 0-11 converters, 12-19 epilogue, 20/21 tile MMA issue (even / odd tiles, one elected lane
 // each), 22 GEMM1 issue, 23 producers (lane 0: x tiles by TMA, lane 1: mode images by bulk copy).  All hand-offs are
-// mbarriers.  MMA issue is the critical path (FNO_FZ_TRACE timeline: an mbarrier wait costs the issuing thread ~300 cycles
-// even when already complete), so a tile's three inputs -- x tile, Zt operand, drained accumulator -- share ONE ring of 6
-// slots and ONE "ready" barrier (TMA bytes + 12 converter arrivals + 8 epilogue arrivals) and three threads issue.
+// mbarriers.  The dependent chain per tile is what limits the kernel (no pipe is saturated: DESIGN.md 4.1), so a tile's three
+// inputs -- x tile, Zt operand, drained accumulator -- share ONE ring of 3 super-slots (2 tiles each) and ONE "ready"
+// barrier (TMA bytes + 12 converter arrivals + 4 epilogue arrivals), three threads issue MMAs, and the next unit's GEMM1 is
+// paced behind the current unit's super-tiles in the in-order tensor queue.
 #include "fno_common.cuh"
 #include "tc_common.cuh"
 #include "tc_tma.cuh"
@@ -289,7 +290,7 @@ __global__ void __launch_bounds__(kFzThreads, 1)
   // ================================================================ epilogue
   // Two groups of four warps (one warp per TMEM lane quadrant) take alternate super-tiles; a thread owns one pixel of each
   // tile and all 32 output channels of it: one barrier wait per super-tile, one tcgen05.ld per tile, 16 independent GELU
-  // pairs per tile (the fixed latencies -- ~300 cycles per wait, ~270 per TMEM read -- dominate the epilogue otherwise).
+  // pairs per tile (the fixed latencies -- barrier wake-up, ~270 cycles per TMEM read -- dominate the epilogue otherwise).
   else if (warp < kFzConvWarps + kFzEpiWarps) {
     const int q = warp & 3, grp = (warp - kFzConvWarps) >> 2;
     const uint32_t lane_base = static_cast<uint32_t>(q * 32) << 16;
@@ -331,8 +332,8 @@ __global__ void __launch_bounds__(kFzThreads, 1)
     }
   }
   // ================================================================ MMA issue: tiles
-  // Two issuing threads (warps 20 / 21) take alternate super-tiles: the ready-wait costs ~300 cycles even when complete,
-  // so one thread alone could not keep the tensor pipe (~620 cycles per tile) fed.  Each thread commits only its own
+  // Two issuing threads (warps 20 / 21) take alternate super-tiles, so that one can wait for its super-tile's inputs while
+  // the other's MMAs are being queued.  Each thread commits only its own
   // super-tile's barriers (tcgen05.commit tracks the MMAs of the executing thread).
   else if (warp == kFzMmaWarp || warp == kFzMmaWarp + 1) {
     if (tc::elect_one()) {
