@@ -271,13 +271,20 @@ def timed_train_step(p: int, batch_size: int, steps: int = 5, warmup: int = 3, f
             ev.append((a, z))
     torch.cuda.synchronize(model.device)
     ms = float(np.median([a.elapsed_time(z) for a, z in ev]))
+    dp_mode = getattr(model, "dp_segments", "one")
     del model
     torch.cuda.empty_cache()
     world = torch.distributed.get_world_size() if torch.distributed.is_initialized() else 1
+    return _train_result(ms, batch_size, world, problem, fused_adam, act, dp_mode)
+
+
+def _train_result(ms, batch_size, world, problem, fused_adam, act, dp_mode):
+    dp_text = {"one": "ONE NCCL AVG all-reduce of the flat gradient buffer after backward",
+               "two": "NCCL AVG in two segments, the first overlapped with the rest of backward",
+               "all": "NCCL AVG per gradient segment, overlapped with the rest of backward"}.get(dp_mode, dp_mode)
     return {"value": 1e3 / ms, "unit": "train steps/s per GPU", "ms_per_step": ms, "batch_per_gpu": batch_size,
             "global_batch": batch_size * world, "problem": problem,
-            "what": "fwd + native MseLoss + nmse.backward" + (" + gradient all-reduce (NCCL AVG, per-segment, overlapped "
-                                                               "with the rest of backward)" if world > 1 else "") +
+            "what": "fwd + native MseLoss + nmse.backward" + (f" + gradient all-reduce ({dp_text})" if world > 1 else "") +
                     " + " + ("FusedAdam (fno_adam_step)" if fused_adam else "torch.optim.Adam") + f".step, {act} storage"}
 
 
