@@ -129,6 +129,33 @@ def test_mode_mix_image_kernel(lib):
     assert np.abs(got - plain).max() <= 2.0 ** -21 * np.abs(plain).max()
 
 
+def test_mode_mix_ring_recycling_large_batch(lib):
+    """700 samples = 6 sample tiles per mode, 12 tiles per CTA: the 4-slot A ring, the 4 accumulators and the 4 lo-operand
+    blocks in tensor memory are each reused three times, the B ring's two slots hold the CTA's two modes (ragged last tile).
+    Both outputs (mode-major ym, per-sample operand image) against float64 on a sample of modes."""
+    from cfdbench_b200 import _lib
+    rng = np.random.default_rng(12)
+    batch = 700
+    sd = synth.make_state_dict(5, spectral_gain=100.0)
+    w1, w2 = sd["blocks.1.conv0.weights1"], sd["blocks.1.conv0.weights2"]
+    xm = (rng.standard_normal((288, batch, 32)) + 1j * rng.standard_normal((288, batch, 32))).astype(np.complex64)
+    w1d, w2d, xmd = dev(w1), dev(w2), dev(xm)
+    wop = torch.empty(lib.fno_mix_operand_bytes(), dtype=torch.uint8, device="cuda")
+    _lib.check(lib.fno_pack_mix_operand_from_weights(w1d.data_ptr(), w2d.data_ptr(), wop.data_ptr(), 0, stream()), "pack")
+    ym = torch.zeros(288, batch, 32, dtype=torch.complex64, device="cuda")
+    _lib.check(lib.fno_mode_mix(xmd.data_ptr(), wop.data_ptr(), ym.data_ptr(), batch, stream()), "mix")
+    wt = onp.stack_weights(w1, w2).reshape(32, 32, 288)
+    modes = [0, 1, 147, 148, 149, 200, 286, 287]   # first / second round of the 148 CTAs, last modes
+    ref = np.einsum("kbi,iok->kbo", xm[modes].astype(np.complex128), wt[:, :, modes])
+    got = ym.cpu().numpy()
+    assert np.linalg.norm(got[modes] - ref) / np.linalg.norm(ref) < 2e-6
+    img = torch.zeros(lib.fno_ym_image_bytes(batch), dtype=torch.uint8, device="cuda")
+    _lib.check(lib.fno_mode_mix_image(xmd.data_ptr(), wop.data_ptr(), img.data_ptr(), batch, stream()), "mix image")
+    dec, _ = decode_ym_image(img.cpu().numpy(), batch)
+    plain = got.transpose(1, 2, 0).reshape(batch, 32, 24, 12)
+    assert np.abs(dec - plain).max() <= 2.0 ** -21 * np.abs(plain).max()
+
+
 @pytest.mark.parametrize("batch", [1, 3, 80])
 def test_block_fused_kernel(lib, batch):
     """irfft2 (both stages on tensor cores, Z kept on chip) + 1x1 conv + bias + GELU, bf16 in / bf16 out.
