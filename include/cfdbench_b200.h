@@ -100,9 +100,10 @@ int fno_lift_fwd(const float* inputs, const float* mask, const float* case_param
 /* The four phases of SpectralConv2d_fast + FnoBlock (reference fno2d.py:59-82, 106-112):            */
 /* (1) torch.fft.rfft2 restricted to the kept modes (fno2d.py:62,73-78); outputs scaled by s0 (ky=0), s1 (ky>0) */
 int fno_spectral_dft_fwd(const void* act_in, void* xm, int batch, int act_dtype, float s0, float s1, void* stream);
-/* (1') the same transform for bf16 planes as two chained tensor-core GEMMs (fno_dft_fwd_tc.cu).  Correct to the same
- *      2e-6, but at 43 us per launch (B=256) not yet faster than the register-FFT kernel (35 us), so the forward
- *      path does not call it; kept as an entry point for the parity test and for round 2. */
+/* (1') the same transform for bf16 planes as two chained tensor-core GEMMs (fno_dft_fwd_tc.cu, warp-specialised since
+ *      round 2: 25 us per launch at B=256 against 35 us for the register-FFT kernel, same 2e-6 against float64).
+ *      fno_spectral_dft_fwd(..., FNO_ACT_BF16, ...) routes here (environment FNO_DFT_TC=0 selects the register kernel for
+ *      A/B measurements); this entry point calls it directly. */
 int fno_spectral_dft_fwd_tc(const void* act_in_bf16, void* xm, int batch, float s0, float s1, void* stream);
 /* (2) einsum("bixy,ioxy->boxy") on both corners (fno2d.py:54-57,73-78); wop = fno_pack_mix_operand image */
 int fno_mode_mix(const void* xm, const void* wop, void* ym, int batch, void* stream);
