@@ -38,14 +38,13 @@
 
 namespace fno {
 
-constexpr int kTdThreads = 800;
+constexpr int kTdThreads = 832;
 constexpr int kTdConvWarps = 16;
 constexpr int kTdEpiWarp0 = 16;      // group 0: warps 16, 17, 18; group 1: warps 20, 21, 22 (lane quadrants 0, 1, 2)
-constexpr int kTdMmaAWarp = 19, kTdMmaBWarp = 23, kTdProdWarp = 24;
+constexpr int kTdMmaAWarp = 19, kTdMmaBWarp = 23 /* and 24: even / odd batches */, kTdProdWarp = 25;
 constexpr int kTdPlanes = 4;                               // planes per batch
-constexpr int kTdR = 4;                                    // x ring slots, one plane PAIR each (the M = 128 operand of stage A)
-constexpr uint32_t kTdXBytes = 2 * kHW * 2;                // 16,384 B per plane pair
-constexpr int kTdNB2 = 3;                                  // stage-B operand buffers
+constexpr int kTdR = 3;                                    // x ring slots
+constexpr uint32_t kTdXBytes = kTdPlanes * kHW * 2;        // 32,768 B per batch
 constexpr int kTdNA = 80;                                  // stage A N: 3 terms x 24, padded to a multiple of 16
 constexpr uint32_t kTdLboTA = (kTdNA / 8) * 128;           // 1280: K stride of the TA operand (8-element chunks)
 constexpr uint32_t kTdTABytes = 8 * kTdLboTA;              // 10,240 B
@@ -89,10 +88,10 @@ __device__ int g_td_knock = 0;   // knock-out experiments (results are wrong): 1
 struct TdSmem {
   alignas(1024) unsigned char x[kTdR][kTdXBytes];       // stage-A A operands (TMA, 128B swizzle)
   alignas(128) unsigned char ta[kTdTABytes];            // stage-A B operand: three bf16 terms, K-major
-  alignas(128) unsigned char b2[kTdNB2][2][kTdB2Bytes]; // stage-B B operand: [buffer][tf32 hi, lo]
+  alignas(128) unsigned char b2[2][2][kTdB2Bytes];      // stage-B B operand: [buffer][tf32 hi, lo]
   alignas(8) uint64_t x_full[kTdR], x_free[kTdR];
   uint64_t da_full[2], da_free[2];
-  uint64_t b2_ready[kTdNB2], b2_free[kTdNB2];
+  uint64_t b2_ready[2], b2_free[2];
   uint64_t db_full[2], db_free[2];
   uint64_t ta_bar;
   uint32_t tmem_base;
@@ -141,13 +140,11 @@ __global__ void __launch_bounds__(kTdThreads, 1)
   // ---------------------------------------------------------------- prologue (constant tables only)
   if (tid == 0) {
     for (int i = 0; i < kTdR; ++i) { mbar_init(&sm.x_full[i], 1); mbar_init(&sm.x_free[i], 1); }
-    for (int i = 0; i < kTdNB2; ++i) {
-      mbar_init(&sm.b2_ready[i], kTdConvWarps);
-      mbar_init(&sm.b2_free[i], 1);
-    }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&sm.da_full[i], 1);
       mbar_init(&sm.da_free[i], kTdConvWarps);
+      mbar_init(&sm.b2_ready[i], kTdConvWarps);
+      mbar_init(&sm.b2_free[i], 1);
       mbar_init(&sm.db_full[i], 1);
       mbar_init(&sm.db_free[i], 3);
     }
@@ -202,30 +199,25 @@ __global__ void __launch_bounds__(kTdThreads, 1)
       __syncwarp();
       if (lane == 0) mbar_arrive(&sm.da_free[i & 1]);   // D_A drained: stage A of batch i + 2 may overwrite it
       if (tid == 0) TD_T(0, i, 2);
-      // sum of the three terms and the tf32 split happen BEFORE the wait for the operand buffer: only the stores need it
-      // tf32 split with a truncated hi (one LOP; the residual is exact) and a rounded lo whose low bits the tensor core
-      // drops itself: 3 instructions per element instead of 5, |g - hi - lo| <= 2^-22 |g| as before
-      float hi[12], lo[12];
+      if (i >= 2) mbar_wait(&sm.b2_free[i & 1], ((i >> 1) - 1) & 1);   // stage B of batch i-2 has consumed this buffer
+      if (tid == 0) TD_T(0, i, 3);
+      unsigned char* hi_p = dst0 + (i & 1) * 2 * kTdB2Bytes;
 #pragma unroll
       for (int jj = 0; jj < 12; ++jj) {
         const float gsum = (v[24 + jj] + v[12 + jj]) + v[jj];
-        hi[jj] = __uint_as_float(__float_as_uint(gsum) & 0xffffe000u);
-        lo[jj] = __uint_as_float(__float_as_uint(gsum - hi[jj]) + 0x1000u);
-      }
-      if (i >= kTdNB2) mbar_wait(&sm.b2_free[i % kTdNB2], ((i / kTdNB2) - 1) & 1);   // stage B of batch i-3 has consumed this buffer
-      if (tid == 0) TD_T(0, i, 3);
-      unsigned char* hi_p = dst0 + (i % kTdNB2) * 2 * kTdB2Bytes;
-#pragma unroll
-      for (int jj = 0; jj < 12; ++jj) {
+        // tf32 split with a truncated hi (one LOP; the residual is exact) and a rounded lo whose low bits the tensor core
+        // drops itself: 3 instructions per element instead of 5, |g - hi - lo| <= 2^-22 |g| as before
+        const float hi = __uint_as_float(__float_as_uint(gsum) & 0xffffe000u);
+        const float lo = __uint_as_float(__float_as_uint(gsum - hi) + 0x1000u);
         constexpr uint32_t kRiStep = 16 * kTdLboB2;  // k2 += 64
         const uint32_t off = (jj & 1) * kRiStep + (jj >> 2) * 128 + ((jj >> 1) & 1) * 64;
         if (TD_KNOCK(2)) continue;
-        *reinterpret_cast<float*>(hi_p + off) = hi[jj];
-        *reinterpret_cast<float*>(hi_p + kTdB2Bytes + off) = lo[jj];
+        *reinterpret_cast<float*>(hi_p + off) = hi;
+        *reinterpret_cast<float*>(hi_p + kTdB2Bytes + off) = lo;
       }
       tc::fence_proxy_async_smem();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&sm.b2_ready[i % kTdNB2]);
+      if (lane == 0) mbar_arrive(&sm.b2_ready[i & 1]);
       if (tid == 0) TD_T(0, i, 4);
     }
   }
@@ -301,27 +293,26 @@ __global__ void __launch_bounds__(kTdThreads, 1)
       mbar_wait(&sm.ta_bar, 0);
 #pragma unroll 1
       for (int i = 0; i < n_mine; ++i) {
+        const int s = i % kTdR;
         TD_T(2, i, 0);
-        if (i >= 2) mbar_wait(&sm.da_free[i & 1], ((i >> 1) - 1) & 1);
+        mbar_wait(&sm.x_full[s], (i / kTdR) & 1);
         TD_T(2, i, 1);
+        if (i >= 2) mbar_wait(&sm.da_free[i & 1], ((i >> 1) - 1) & 1);
+        tc::fence_after_thread_sync();
+        TD_T(2, i, 2);
+        const uint32_t x_s = tc::smem_addr(sm.x[s]);
 #pragma unroll
         for (int g = 0; g < 2; ++g) {
-          const int j = 2 * i + g, s = j % kTdR;   // plane pair j of this CTA
-          mbar_wait(&sm.x_full[s], (j / kTdR) & 1);
-          tc::fence_after_thread_sync();
-          if (g == 0) TD_T(2, i, 2);
-          if (!TD_KNOCK(8)) {
-            const uint32_t x_s = tc::smem_addr(sm.x[s]);
-            const uint32_t d = tmem + kTdColDA + (i & 1) * (2 * kTdNA) + g * kTdNA;
+          if (TD_KNOCK(8)) break;
+          const uint32_t d = tmem + kTdColDA + (i & 1) * (2 * kTdNA) + g * kTdNA;
 #pragma unroll
-            for (int ks = 0; ks < 4; ++ks) {   // K = 16 per MMA: 32 bytes inside the 128-byte swizzle row / two 8-element chunks
-              const uint64_t da = fz_desc_sw128(x_s + ks * 32, 0, 1024);
-              const uint64_t db = tc::make_smem_desc(ta_s + ks * 2 * kTdLboTA, kTdLboTA, 128);
-              fz_mma_f16_ss(d, da, db, idesc, ks ? 1u : 0u);
-            }
+          for (int ks = 0; ks < 4; ++ks) {   // K = 16 per MMA: 32 bytes inside the 128-byte swizzle row / two 8-element chunks
+            const uint64_t da = fz_desc_sw128(x_s + g * (2 * kHW * 2) + ks * 32, 0, 1024);
+            const uint64_t db = tc::make_smem_desc(ta_s + ks * 2 * kTdLboTA, kTdLboTA, 128);
+            fz_mma_f16_ss(d, da, db, idesc, ks ? 1u : 0u);
           }
-          tc::mma_commit(&sm.x_free[s]);
         }
+        tc::mma_commit(&sm.x_free[s]);
         tc::mma_commit(&sm.da_full[i & 1]);
         TD_T(2, i, 3);
       }
@@ -329,16 +320,18 @@ __global__ void __launch_bounds__(kTdThreads, 1)
     __syncwarp();
   }
   // ================================================================ MMA issue: stage B
-  else if (warp == kTdMmaBWarp) {
+  // two issuing threads (even / odd batches, each with its own accumulator and operand buffer): one waits for its
+  // operands while the other's MMAs are being queued
+  else if (warp == kTdMmaBWarp || warp == kTdMmaBWarp + 1) {
     if (tc::elect_one()) {
       constexpr uint32_t idesc = tc::make_idesc_tf32(128, kTdN2);
 #pragma unroll 1
-      for (int i = 0; i < n_mine; ++i) {
-        const int bf = i % kTdNB2;
+      for (int i = warp - kTdMmaBWarp; i < n_mine; i += 2) {
+        const int bf = i & 1;
         TD_T(3, i, 0);
-        mbar_wait(&sm.b2_ready[bf], (i / kTdNB2) & 1);
+        mbar_wait(&sm.b2_ready[bf], (i >> 1) & 1);
         TD_T(3, i, 1);
-        if (i >= 1) mbar_wait(&sm.db_free[(i - 1) & 1], ((i - 1) >> 1) & 1);   // the previous batch has left the accumulator
+        if (i >= 1) mbar_wait(&sm.db_free[bf ^ 1], ((i - 1) >> 1) & 1);   // the previous batch has left the accumulator
         tc::fence_after_thread_sync();
         TD_T(3, i, 2);
         const uint32_t d = tmem + kTdColDB;
@@ -353,7 +346,7 @@ __global__ void __launch_bounds__(kTdThreads, 1)
                            (pass | ks) ? 1u : 0u);
         }
         tc::mma_commit(&sm.b2_free[bf]);
-        tc::mma_commit(&sm.db_full[i & 1]);
+        tc::mma_commit(&sm.db_full[bf]);
         TD_T(3, i, 3);
       }
     }
@@ -362,13 +355,13 @@ __global__ void __launch_bounds__(kTdThreads, 1)
   // ================================================================ producer
   else if (warp == kTdProdWarp) {
     if (lane == 0) {
-      for (int j = 0; j < 2 * n_mine; ++j) {   // plane pairs
-        const int s = j % kTdR, i = j >> 1;
-        if ((j & 1) == 0) TD_T(4, i, 0);
-        if (j >= kTdR) mbar_wait(&sm.x_free[s], ((j / kTdR) - 1) & 1);
-        if ((j & 1) == 0) TD_T(4, i, 1);
+      for (int i = 0; i < n_mine; ++i) {
+        const int s = i % kTdR;
+        TD_T(4, i, 0);
+        if (i >= kTdR) mbar_wait(&sm.x_free[s], ((i / kTdR) - 1) & 1);
+        TD_T(4, i, 1);
         mbar_expect_tx(&sm.x_full[s], kTdXBytes);
-        fz_tma_load_2d(sm.x[s], &x_map, 0, (first + i * stride) * (kTdPlanes * kH) + (j & 1) * (2 * kH), &sm.x_full[s]);
+        fz_tma_load_2d(sm.x[s], &x_map, 0, (first + i * stride) * (kTdPlanes * kH), &sm.x_full[s]);
       }
     }
     __syncwarp();
@@ -503,7 +496,7 @@ static cudaError_t td_make_map(const void* act, int batch, CUtensorMap* out) {
   }
   const cuuint64_t gdim[2] = {static_cast<cuuint64_t>(kW), static_cast<cuuint64_t>(batch) * kC * kH};
   const cuuint64_t gstride[1] = {static_cast<cuuint64_t>(kW) * 2};
-  const cuuint32_t box[2] = {static_cast<cuuint32_t>(kW), static_cast<cuuint32_t>(2 * kH)}, estr[2] = {1, 1};
+  const cuuint32_t box[2] = {static_cast<cuuint32_t>(kW), static_cast<cuuint32_t>(kTdPlanes * kH)}, estr[2] = {1, 1};
   const CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(act), gdim, gstride, box, estr,
                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
