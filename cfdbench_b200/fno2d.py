@@ -169,6 +169,7 @@ class Fno2d(AutoCfdModel):
         # streams over 2 batch chunks 0.753 ms, over 4 chunks 0.842 ms (chunks of 64 run the 14 kernels at their fixed
         # costs); kernels reading / writing the pinned host buffers directly 0.796 ms (1 chunk) / 0.815 / 0.881 ms
         self.host_chunks = 2
+        self.host_chunk_plan = None   # e.g. (0.25, 0.75): uneven chunks (short exposed upload, see tools/e2e_sweep.py)
         self.host_zero_copy = False  # opt-in: lift reads the pinned frame, project writes the pinned result directly
         self.zero_copy_chunks = 2
         self._graphs: dict = {}
@@ -597,7 +598,18 @@ class Fno2d(AutoCfdModel):
         out = torch.empty(steps, b, self.out_chan, H, W, dtype=torch.float32, pin_memory=True)
         if steps == 1 and self.host_zero_copy and inputs.is_pinned() and b >= 8:
             return self._step_host_zero_copy(inputs, case_params, mask3, out, pk)
-        n_chunks = self.host_chunks if (steps == 1 and b >= 128 and b % self.host_chunks == 0) else 1
+        # chunk plan of a single large step: explicit fractions (host_chunk_plan, e.g. (0.25, 0.75)) or host_chunks equal parts
+        sizes = [b]
+        if steps == 1 and b >= 128:
+            if self.host_chunk_plan is not None:
+                sizes = [int(round(f * b)) for f in self.host_chunk_plan]
+                sizes[-1] = b - sum(sizes[:-1])
+                if min(sizes) < 8:
+                    sizes = [b]
+            elif b % self.host_chunks == 0:
+                sizes = [b // self.host_chunks] * self.host_chunks
+        n_chunks = len(sizes)
+        offs = [sum(sizes[:c]) for c in range(n_chunks)]
         if n_chunks == 1:
             key = ("host_io", b, steps)
             ent = self._ws_cache.get(key)
@@ -613,16 +625,15 @@ class Fno2d(AutoCfdModel):
             cur.synchronize()
             return out
 
-        cb = b // n_chunks
-        key = ("host_chunked", b, n_chunks, self.act_dtype, self.fused_block)
+        key = ("host_chunked", b, tuple(sizes), self.act_dtype, self.fused_block)
         ent = self._ws_cache.get(key)
         if ent is None or ent["pk"] is not pk:
             ent = dict(
                 pk=pk,
-                d_in=[torch.empty(cb, self.in_chan, H, W, dtype=torch.float32, device=dev) for _ in range(n_chunks)],
+                d_in=[torch.empty(cb, self.in_chan, H, W, dtype=torch.float32, device=dev) for cb in sizes],
                 d_mask=torch.empty(b, 1, H, W, dtype=torch.float32, device=dev),
                 d_cp=torch.empty(b, max(self.n_case_params, 1), dtype=torch.float32, device=dev),
-                d_out=[torch.empty(cb, self.out_chan, H, W, dtype=torch.float32, device=dev) for _ in range(n_chunks)],
+                d_out=[torch.empty(cb, self.out_chan, H, W, dtype=torch.float32, device=dev) for cb in sizes],
                 streams=[torch.cuda.Stream(device=dev) for _ in range(3)],
                 ev_in=[torch.cuda.Event() for _ in range(n_chunks)], ev_cmp=[torch.cuda.Event() for _ in range(n_chunks)],
                 graphs=None, inv_key=None,
@@ -643,16 +654,17 @@ class Fno2d(AutoCfdModel):
             s_cmp.wait_stream(s_in)
             with torch.cuda.stream(s_cmp):
                 for c in range(n_chunks):
+                    cb, lo = sizes[c], offs[c]
                     ws, _ = self._workspace(cb, slot=1 + c)
-                    cp_c = ent["d_cp"][c * cb:(c + 1) * cb]
+                    cp_c = ent["d_cp"][lo:lo + cb]
                     assert cp_c.is_contiguous() or self.n_case_params == 0
                     if self.n_case_params not in (0, ent["d_cp"].shape[1]):
                         raise _lib.FnoNativeError("internal: case-parameter staging width")
 
-                    def run(c=c, ws=ws):
+                    def run(c=c, ws=ws, cb=cb, lo=lo):
                         _lib.check(lib.fno_forward(C.byref(pk["struct"]), ent["d_in"][c].data_ptr(),
-                                                   ent["d_mask"][c * cb:(c + 1) * cb].data_ptr(),
-                                                   ent["d_cp"][c * cb:(c + 1) * cb].data_ptr(), ent["d_out"][c].data_ptr(),
+                                                   ent["d_mask"][lo:lo + cb].data_ptr(),
+                                                   ent["d_cp"][lo:lo + cb].data_ptr(), ent["d_out"][c].data_ptr(),
                                                    C.byref(ws), cb, self._act_code(),
                                                    C.c_void_p(s_cmp.cuda_stream)), "fno_forward")
                     run()   # warm-up outside capture (kernel attributes, constant tables)
@@ -668,7 +680,7 @@ class Fno2d(AutoCfdModel):
         out2 = out.view(b, self.out_chan, H, W)
         for c in range(n_chunks):
             with torch.cuda.stream(s_in):
-                ent["d_in"][c].copy_(inputs[c * cb:(c + 1) * cb], non_blocking=True)
+                ent["d_in"][c].copy_(inputs[offs[c]:offs[c] + sizes[c]], non_blocking=True)
                 ent["ev_in"][c].record(s_in)
         for c in range(n_chunks):
             s_cmp.wait_event(ent["ev_in"][c])
@@ -678,6 +690,6 @@ class Fno2d(AutoCfdModel):
         for c in range(n_chunks):
             s_out.wait_event(ent["ev_cmp"][c])
             with torch.cuda.stream(s_out):
-                out2[c * cb:(c + 1) * cb].copy_(ent["d_out"][c], non_blocking=True)
+                out2[offs[c]:offs[c] + sizes[c]].copy_(ent["d_out"][c], non_blocking=True)
         s_out.synchronize()
         return out
