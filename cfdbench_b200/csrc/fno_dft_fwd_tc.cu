@@ -199,21 +199,26 @@ __global__ void __launch_bounds__(kTdThreads, 1)
       __syncwarp();
       if (lane == 0) mbar_arrive(&sm.da_free[i & 1]);   // D_A drained: stage A of batch i + 2 may overwrite it
       if (tid == 0) TD_T(0, i, 2);
+      // sum of the three terms and the tf32 split happen BEFORE the wait for the operand buffer: only the stores need it
+      // tf32 split with a truncated hi (one LOP; the residual is exact) and a rounded lo whose low bits the tensor core
+      // drops itself: 3 instructions per element instead of 5, |g - hi - lo| <= 2^-22 |g| as before
+      float hi[12], lo[12];
+#pragma unroll
+      for (int jj = 0; jj < 12; ++jj) {
+        const float gsum = (v[24 + jj] + v[12 + jj]) + v[jj];
+        hi[jj] = __uint_as_float(__float_as_uint(gsum) & 0xffffe000u);
+        lo[jj] = __uint_as_float(__float_as_uint(gsum - hi[jj]) + 0x1000u);
+      }
       if (i >= 2) mbar_wait(&sm.b2_free[i & 1], ((i >> 1) - 1) & 1);   // stage B of batch i-2 has consumed this buffer
       if (tid == 0) TD_T(0, i, 3);
       unsigned char* hi_p = dst0 + (i & 1) * 2 * kTdB2Bytes;
 #pragma unroll
       for (int jj = 0; jj < 12; ++jj) {
-        const float gsum = (v[24 + jj] + v[12 + jj]) + v[jj];
-        // tf32 split with a truncated hi (one LOP; the residual is exact) and a rounded lo whose low bits the tensor core
-        // drops itself: 3 instructions per element instead of 5, |g - hi - lo| <= 2^-22 |g| as before
-        const float hi = __uint_as_float(__float_as_uint(gsum) & 0xffffe000u);
-        const float lo = __uint_as_float(__float_as_uint(gsum - hi) + 0x1000u);
         constexpr uint32_t kRiStep = 16 * kTdLboB2;  // k2 += 64
         const uint32_t off = (jj & 1) * kRiStep + (jj >> 2) * 128 + ((jj >> 1) & 1) * 64;
         if (TD_KNOCK(2)) continue;
-        *reinterpret_cast<float*>(hi_p + off) = hi;
-        *reinterpret_cast<float*>(hi_p + kTdB2Bytes + off) = lo;
+        *reinterpret_cast<float*>(hi_p + off) = hi[jj];
+        *reinterpret_cast<float*>(hi_p + kTdB2Bytes + off) = lo[jj];
       }
       tc::fence_proxy_async_smem();
       __syncwarp();
