@@ -41,7 +41,7 @@ cudaError_t launch_project_bwd(const void*, const float*, const float*, const fl
                                const float*, float*, float*, float*, int, cudaStream_t);
 int project_bwd_parts(int);
 int project_bwd_row();
-cudaError_t launch_reduce_partials(const float*, int, int, int, float*, cudaStream_t);
+cudaError_t launch_reduce_partials(const float*, int, int, float*, int, float*, int, float*, int, cudaStream_t);
 template <typename TP, typename TQ, int NJ, int NI>
 cudaError_t launch_chan_outer(const void*, const void*, float*, int*, int, cudaStream_t);
 cudaError_t launch_multistep_metrics(const float*, const float*, const float*, float*, int, int, cudaStream_t);
@@ -418,14 +418,14 @@ int fno_backward_ex(const fno_weights* w, const fno_weights_bwd* wb, const float
            : launch_project_bwd<float>(a_l, dp, mk, pre, w->fc1_w, w->fc1_b, w->fc2_w, dout, sc->dz1, part_pb, nb, st);
     FNO_CUDA(e, "project_bwd_kernel");
     const int rows = project_bwd_parts(nb), rs = project_bwd_row();
-    FNO_CUDA(launch_reduce_partials(part_pb, rows, 2 * kProj, rs, g->fc2_w, st), "reduce(fc2.weight)");
-    FNO_CUDA(launch_reduce_partials(part_pb + 2 * kProj, rows, kProj, rs, g->fc1_b, st), "reduce(fc1.bias)");
-    FNO_CUDA(launch_reduce_partials(part_pb + 3 * kProj, rows, 2, rs, g->fc2_b, st), "reduce(fc2.bias)");
+    FNO_CUDA(launch_reduce_partials(part_pb, rows, rs, g->fc2_w, 2 * kProj, g->fc1_b, kProj, g->fc2_b, 2, st),
+             "reduce(fc2.weight | fc1.bias | fc2.bias)");
     int n_co = 0;
     e = bf ? launch_chan_outer<float, __nv_bfloat16, 128, 32>(sc->dz1, a_l, part_co, &n_co, nb, st)
            : launch_chan_outer<float, float, 128, 32>(sc->dz1, a_l, part_co, &n_co, nb, st);
     FNO_CUDA(e, "chan_outer_kernel(fc1)");
-    FNO_CUDA(launch_reduce_partials(part_co, n_co, kProj * kC, kProj * kC + kProj, g->fc1_w, st), "reduce(fc1.weight)");
+    FNO_CUDA(launch_reduce_partials(part_co, n_co, kProj * kC + kProj, g->fc1_w, kProj * kC, nullptr, 0, nullptr, 0, st),
+             "reduce(fc1.weight)");
   }
   auto mark = [&](int seg) -> cudaError_t {   // the gradients of segment `seg` are final from here on (stream order)
     if (seg_events == nullptr || seg_events[seg] == nullptr) return cudaSuccess;
@@ -442,8 +442,8 @@ int fno_backward_ex(const fno_weights* w, const fno_weights_bwd* wb, const float
     cudaError_t e = bf ? launch_chan_outer<float, __nv_bfloat16, 32, 32>(dpre, saved->act[l], part_co, &n_co, batch, st)
                        : launch_chan_outer<float, float, 32, 32>(dpre, saved->act[l], part_co, &n_co, batch, st);
     FNO_CUDA(e, "chan_outer_kernel(w0)");
-    FNO_CUDA(launch_reduce_partials(part_co, n_co, kC * kC, kC * kC + kC, g->w0_w[l], st), "reduce(w0.weight)");
-    FNO_CUDA(launch_reduce_partials(part_co + kC * kC, n_co, kC, kC * kC + kC, g->w0_b[l], st), "reduce(w0.bias)");
+    FNO_CUDA(launch_reduce_partials(part_co, n_co, kC * kC + kC, g->w0_w[l], kC * kC, g->w0_b[l], kC, nullptr, 0, st),
+             "reduce(w0.weight | w0.bias)");
     FNO_TRY(fno_spectral_dft_fwd(dpre, sc->gm, batch, FNO_ACT_F32, inv, 2.f * inv, stream));
     FNO_CUDA(launch_spectral_wgrad(saved->xm[l], sc->gm, sc->gwk, batch, st), "spectral_wgrad_kernel");
     FNO_TRY(fno_unpack_spectral_grads(sc->gwk, g->spec_w1[l], g->spec_w2[l], stream));

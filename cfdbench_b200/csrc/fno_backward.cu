@@ -34,40 +34,51 @@ constexpr int kPbThreads = 128;
 constexpr int kPbPix = 256;
 constexpr int kPbOut = 3 * kProj + 2;   // per-CTA partial row: g_w2 (2 x 128) | g_b1 (128) | g_b2 (2)
 
-// out[i] += sum over parts (in index order) of partial[part][i]: the second, deterministic half of every small-gradient
+// out[i] += sum over parts of partial[part][i] in a FIXED order: the second, deterministic half of every small-gradient
 // reduction (the first half = one plain store per CTA).  Replaces float atomics, whose summation order -- and therefore the
 // last bits of every gradient and the whole training trajectory -- changed from run to run.
-__global__ void __launch_bounds__(256) reduce_partials_kernel(const float* __restrict__ partial, int n_parts, int n_out,
-                                                              int row_stride, float* __restrict__ out) {
-  // block = 32 columns x 8 row groups: thread (tx, ty) adds rows ty, ty+8, .. (four independent loads in flight), the
-  // eight group sums are then added in index order -> a fixed summation tree, independent of scheduling
-  __shared__ float red[8][33];
+// One launch serves up to three consecutive column segments of the partial rows, each with its own destination (e.g. the
+// w2 | b1 | b2 gradients of project_bwd's 386-column rows).  Block = 32 columns x 32 row groups: thread (tx, ty) adds rows
+// ty, ty + 32, .. with all its loads in flight (the first version had 8 row groups and ~37 dependent loads per thread:
+// 14.5 us per launch, 16 launches per training step), the 32 group sums are then added in index order.
+struct ReduceSeg {
+  float* out[3];
+  int n[3];
+};
+__global__ void __launch_bounds__(1024) reduce_partials_kernel(const float* __restrict__ partial, int n_parts, int row_stride,
+                                                               ReduceSeg seg) {
+  __shared__ float red[32][33];
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
   const int i = blockIdx.x * 32 + tx;
-  float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+  const int n_out = seg.n[0] + seg.n[1] + seg.n[2];
+  float s[4] = {0.f, 0.f, 0.f, 0.f};
   if (i < n_out) {
-    int c = ty;
-    for (; c + 24 < n_parts; c += 32) {
-      s0 += partial[static_cast<size_t>(c) * row_stride + i];
-      s1 += partial[static_cast<size_t>(c + 8) * row_stride + i];
-      s2 += partial[static_cast<size_t>(c + 16) * row_stride + i];
-      s3 += partial[static_cast<size_t>(c + 24) * row_stride + i];
+    int c = ty, u = 0;
+    for (; c + 96 < n_parts; c += 128) {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) s[k] += partial[static_cast<size_t>(c + 32 * k) * row_stride + i];
     }
-    for (; c < n_parts; c += 8) s0 += partial[static_cast<size_t>(c) * row_stride + i];
+    for (; c < n_parts; c += 32, ++u) s[u & 3] += partial[static_cast<size_t>(c) * row_stride + i];
   }
-  red[ty][tx] = (s0 + s1) + (s2 + s3);
+  red[ty][tx] = (s[0] + s[1]) + (s[2] + s[3]);
   __syncthreads();
   if (ty == 0 && i < n_out) {
-    float s = red[0][tx];
+    float t = red[0][tx];
 #pragma unroll
-    for (int r = 1; r < 8; ++r) s += red[r][tx];
-    out[i] += s;
+    for (int r = 1; r < 32; ++r) t += red[r][tx];
+    if (i < seg.n[0]) seg.out[0][i] += t;
+    else if (i < seg.n[0] + seg.n[1]) seg.out[1][i - seg.n[0]] += t;
+    else seg.out[2][i - seg.n[0] - seg.n[1]] += t;
   }
 }
-cudaError_t launch_reduce_partials(const float* partial, int n_parts, int n_out, int row_stride, float* out,
-                                   cudaStream_t stream) {
+cudaError_t launch_reduce_partials(const float* partial, int n_parts, int row_stride, float* out0, int n0, float* out1, int n1,
+                                   float* out2, int n2, cudaStream_t stream) {
+  const int n_out = n0 + n1 + n2;
   if (n_parts <= 0 || n_out <= 0) return cudaSuccess;
-  reduce_partials_kernel<<<(n_out + 31) / 32, 256, 0, stream>>>(partial, n_parts, n_out, row_stride, out);
+  ReduceSeg seg;
+  seg.out[0] = out0; seg.out[1] = out1; seg.out[2] = out2;
+  seg.n[0] = n0; seg.n[1] = n1; seg.n[2] = n2;
+  reduce_partials_kernel<<<(n_out + 31) / 32, 1024, 0, stream>>>(partial, n_parts, row_stride, seg);
   return cudaGetLastError();
 }
 
@@ -235,35 +246,54 @@ template cudaError_t launch_project_bwd<__nv_bfloat16>(const void*, const float*
 // ------------------------------------------------------------------------------------- chan outer
 // out[j][i] += sum_{b,pix} P[b][j][pix] * Q[b][i][pix];   rowsum[j] += sum_{b,pix} P[b][j][pix]
 constexpr int kCoThreads = 256;
-constexpr int kCoPix = 128;
-constexpr int kCoPitch = kCoPix + 4;
 
+// 4 consecutive pixels of a staged row as fp32 (bf16 rows are widened by a shift)
 template <typename T>
-__device__ __forceinline__ float4 load4(const T* p);
+__device__ __forceinline__ float4 co_ld4(const unsigned char* row, int px);
 template <>
-__device__ __forceinline__ float4 load4<float>(const float* p) {
-  return *reinterpret_cast<const float4*>(p);
+__device__ __forceinline__ float4 co_ld4<float>(const unsigned char* row, int px) {
+  return *reinterpret_cast<const float4*>(row + px * 4);
 }
 template <>
-__device__ __forceinline__ float4 load4<__nv_bfloat16>(const __nv_bfloat16* p) {
-  const uint2 v = *reinterpret_cast<const uint2*>(p);
+__device__ __forceinline__ float4 co_ld4<__nv_bfloat16>(const unsigned char* row, int px) {
+  const uint2 v = *reinterpret_cast<const uint2*>(row + px * 2);
   return make_float4(__uint_as_float(v.x << 16), __uint_as_float(v.x & 0xffff0000u), __uint_as_float(v.y << 16),
                      __uint_as_float(v.y & 0xffff0000u));
 }
+
+// G[j][i] = sum_{b,pix} P[b][j][pix] Q[b][i][pix] and the row sums of P (the bias gradient): the 1x1-convolution weight
+// gradients.  Round 1's version gave every thread a 2x2 (4x4) output tile: one 16-byte shared-memory read per 4 fma, so
+// the kernel ran at the shared-memory rate, a quarter of the fma rate (68 / 98 us per launch at B = 64, 30 % of a
+// training step).  Here a thread owns an 8 x 4 output tile (1.5 B of shared memory per fma) and the pixels of a chunk are
+// split among NG thread groups whose partial tiles are added in a fixed order at the end; chunks arrive through a
+// two-stage cp.async ring, so the loads of the next chunk overlap the arithmetic of the current one.
+// Rows are assigned interleaved (j = a * NJ/8 + tj, i = c * NI/4 + ti) so that the rows a warp reads at the same time are
+// consecutive and, with the 16-byte row skew, fall into different banks.
+template <typename TP, typename TQ, int NJ, int NI>
+struct CoCfg {
+  static constexpr int TJ = 8, TI = 4;
+  static constexpr int G = NJ * NI / (TJ * TI);          // threads per pixel group
+  static constexpr int NG = kCoThreads / G;              // pixel groups
+  static constexpr int PIX = (NJ >= 128) ? 64 : 128;     // pixels per chunk
+  static constexpr int PXG = PIX / NG;                   // pixels per group and chunk
+  static constexpr int NTI = NI / TI, NTJ = NJ / TJ;
+  static constexpr int PITCH_P = PIX * static_cast<int>(sizeof(TP)) + 16, PITCH_Q = PIX * static_cast<int>(sizeof(TQ)) + 16;
+  static constexpr int STAGE = NJ * PITCH_P + NI * PITCH_Q;
+  static constexpr int OUT = NJ * NI + NJ;
+  static constexpr size_t SMEM = (2 * STAGE > NG * OUT * 4) ? 2 * STAGE : NG * OUT * 4;
+  static_assert(G * NG == kCoThreads && PXG % 4 == 0 && NJ % TJ == 0 && NI % TI == 0, "tile mismatch");
+};
 
 template <typename TP, typename TQ, int NJ, int NI>
 __global__ void __launch_bounds__(kCoThreads)
     chan_outer_kernel(const TP* __restrict__ P, const TQ* __restrict__ Q, float* __restrict__ partial, int batch) {
   // partial[CTA][NJ*NI + NJ]: this CTA's share of G[j][i] and of the row sums sum_pix P[j][pix] (the bias gradient)
-  constexpr int TJ = (NJ * NI / kCoThreads >= 16) ? 4 : 2;
-  constexpr int TI = NJ * NI / kCoThreads / TJ;
-  constexpr int NTI = NI / TI;
-  static_assert(TJ * TI * kCoThreads == NJ * NI, "tile mismatch");
-  extern __shared__ __align__(16) float smem_f[];
-  float* ps = smem_f;                    // [NJ][pitch]
-  float* qs = smem_f + NJ * kCoPitch;    // [NI][pitch]
+  using Cfg = CoCfg<TP, TQ, NJ, NI>;
+  constexpr int TJ = Cfg::TJ, TI = Cfg::TI, PIX = Cfg::PIX;
+  extern __shared__ __align__(16) unsigned char co_smem[];
   const int tid = threadIdx.x;
-  const int tj = tid / NTI, ti = tid % NTI;
+  const int grp = tid / Cfg::G, t = tid % Cfg::G;
+  const int tj = t / Cfg::NTI, ti = t % Cfg::NTI;
   float acc[TJ][TI];
   float rs[TJ];
 #pragma unroll
@@ -272,57 +302,86 @@ __global__ void __launch_bounds__(kCoThreads)
 #pragma unroll
     for (int c = 0; c < TI; ++c) acc[a][c] = 0.f;
   }
-  const int chunks = kHW / kCoPix;
+  const int chunks = kHW / PIX;
   const int items = batch * chunks;
-  for (int it = blockIdx.x; it < items; it += gridDim.x) {
-    const int b = it / chunks, p0 = (it % chunks) * kCoPix;
-    __syncthreads();
-    for (int e = tid; e < NJ * (kCoPix / 4); e += kCoThreads) {
-      const int j = e / (kCoPix / 4), q = e % (kCoPix / 4);
-      *reinterpret_cast<float4*>(ps + j * kCoPitch + 4 * q) =
-          load4<TP>(P + (static_cast<size_t>(b) * NJ + j) * kHW + p0 + 4 * q);
+  auto stage_load = [&](int it, int st) {   // all threads: 16-byte cp.async pieces of the item's P and Q rows
+    const int b = it / chunks, p0 = (it % chunks) * PIX;
+    unsigned char* base = co_smem + st * Cfg::STAGE;
+    constexpr int CP = PIX * static_cast<int>(sizeof(TP)) / 16, CQ = PIX * static_cast<int>(sizeof(TQ)) / 16;
+    for (int e = tid; e < NJ * CP; e += kCoThreads) {
+      const int j = e / CP, q = e % CP;
+      const char* src = reinterpret_cast<const char*>(P + (static_cast<size_t>(b) * NJ + j) * kHW + p0) + q * 16;
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(base + j * Cfg::PITCH_P + q * 16)), "l"(src) : "memory");
     }
-    for (int e = tid; e < NI * (kCoPix / 4); e += kCoThreads) {
-      const int i = e / (kCoPix / 4), q = e % (kCoPix / 4);
-      *reinterpret_cast<float4*>(qs + i * kCoPitch + 4 * q) =
-          load4<TQ>(Q + (static_cast<size_t>(b) * NI + i) * kHW + p0 + 4 * q);
+    for (int e = tid; e < NI * CQ; e += kCoThreads) {
+      const int i = e / CQ, q = e % CQ;
+      const char* src = reinterpret_cast<const char*>(Q + (static_cast<size_t>(b) * NI + i) * kHW + p0) + q * 16;
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(base + NJ * Cfg::PITCH_P + i * Cfg::PITCH_Q + q * 16)),
+                   "l"(src) : "memory");
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+  int n = 0;
+  if (static_cast<int>(blockIdx.x) < items) stage_load(blockIdx.x, 0);
+  for (int it = blockIdx.x; it < items; it += gridDim.x, ++n) {
+    const int nxt = it + gridDim.x;
+    if (nxt < items) {
+      stage_load(nxt, (n + 1) & 1);   // the buffer was released by the barrier at the end of the previous iteration
+      asm volatile("cp.async.wait_group 1;" ::: "memory");
+    } else {
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
     }
     __syncthreads();
-#pragma unroll 4
-    for (int q = 0; q < kCoPix / 4; ++q) {
+    const unsigned char* ps = co_smem + (n & 1) * Cfg::STAGE;
+    const unsigned char* qs = ps + NJ * Cfg::PITCH_P;
+#pragma unroll 2
+    for (int q = 0; q < Cfg::PXG / 4; ++q) {
+      const int px = grp * Cfg::PXG + 4 * q;
       float4 pv[TJ], qv[TI];
 #pragma unroll
-      for (int a = 0; a < TJ; ++a) pv[a] = *reinterpret_cast<const float4*>(ps + (tj * TJ + a) * kCoPitch + 4 * q);
+      for (int a = 0; a < TJ; ++a) pv[a] = co_ld4<TP>(ps + (a * Cfg::NTJ + tj) * Cfg::PITCH_P, px);
 #pragma unroll
-      for (int c = 0; c < TI; ++c) qv[c] = *reinterpret_cast<const float4*>(qs + (ti * TI + c) * kCoPitch + 4 * q);
+      for (int c = 0; c < TI; ++c) qv[c] = co_ld4<TQ>(qs + (c * Cfg::NTI + ti) * Cfg::PITCH_Q, px);
 #pragma unroll
       for (int a = 0; a < TJ; ++a) {
-        rs[a] += (pv[a].x + pv[a].y) + (pv[a].z + pv[a].w);
+        if (ti == 0) rs[a] += (pv[a].x + pv[a].y) + (pv[a].z + pv[a].w);
 #pragma unroll
         for (int c = 0; c < TI; ++c)
           acc[a][c] = fmaf(pv[a].x, qv[c].x, fmaf(pv[a].y, qv[c].y, fmaf(pv[a].z, qv[c].z, fmaf(pv[a].w, qv[c].w, acc[a][c]))));
       }
     }
+    __syncthreads();   // everybody is done with this stage: the next iteration may refill it
   }
-  float* prow = partial + static_cast<size_t>(blockIdx.x) * (NJ * NI + NJ);
+  // the NG pixel groups' tiles, added in group order (fixed summation tree)
+  float* red = reinterpret_cast<float*>(co_smem);
 #pragma unroll
   for (int a = 0; a < TJ; ++a) {
+    const int j = a * Cfg::NTJ + tj;
 #pragma unroll
-    for (int c = 0; c < TI; ++c) prow[(tj * TJ + a) * NI + ti * TI + c] = acc[a][c];
-    if (ti == 0) prow[NJ * NI + tj * TJ + a] = rs[a];
+    for (int c = 0; c < TI; ++c) red[grp * Cfg::OUT + j * NI + c * Cfg::NTI + ti] = acc[a][c];
+    if (ti == 0) red[grp * Cfg::OUT + NJ * NI + j] = rs[a];
+  }
+  __syncthreads();
+  float* prow = partial + static_cast<size_t>(blockIdx.x) * Cfg::OUT;
+  for (int e = tid; e < Cfg::OUT; e += kCoThreads) {
+    float v = red[e];
+#pragma unroll
+    for (int g = 1; g < Cfg::NG; ++g) v += red[g * Cfg::OUT + e];
+    prow[e] = v;
   }
 }
 
 // returns the number of partial rows written (= grid size) through *n_parts
 template <typename TP, typename TQ, int NJ, int NI>
 cudaError_t launch_chan_outer(const void* P, const void* Q, float* partial, int* n_parts, int batch, cudaStream_t stream) {
+  using Cfg = CoCfg<TP, TQ, NJ, NI>;
   auto kern = chan_outer_kernel<TP, TQ, NJ, NI>;
-  constexpr size_t smem = static_cast<size_t>(NJ + NI) * kCoPitch * sizeof(float);
+  constexpr size_t smem = Cfg::SMEM;
   static PerDeviceLaunch pd;
   cudaError_t e0 = per_device_setup(kern, smem, pd);
   if (e0 != cudaSuccess) return e0;
-  const int items = batch * (kHW / kCoPix);
-  const int grid = items < 296 ? items : 296;
+  const int items = batch * (kHW / Cfg::PIX);
+  const int grid = items < 296 ? items : 296;   // 2 CTAs per SM; also the row count of the partial buffer
   kern<<<grid, kCoThreads, smem, stream>>>(static_cast<const TP*>(P), static_cast<const TQ*>(Q), partial, batch);
   *n_parts = grid;
   return cudaGetLastError();
