@@ -41,7 +41,7 @@ cudaError_t launch_project_bwd(const void*, const float*, const float*, const fl
                                const float*, float*, float*, float*, int, cudaStream_t);
 int project_bwd_parts(int);
 int project_bwd_row();
-cudaError_t launch_reduce_partials(const float*, int, int, float*, int, float*, int, float*, int, cudaStream_t);
+cudaError_t launch_reduce_partials(const float*, int, int, float*, int, float*, int, float*, int, int, cudaStream_t);
 template <typename TP, typename TQ, int NJ, int NI>
 cudaError_t launch_chan_outer(const void*, const void*, float*, int*, int, cudaStream_t);
 cudaError_t launch_multistep_metrics(const float*, const float*, const float*, float*, int, int, cudaStream_t);
@@ -394,16 +394,8 @@ int fno_backward_ex(const fno_weights* w, const fno_weights_bwd* wb, const float
   float* part_co = sc->partials;                                   // chan_outer: up to 296 rows x (128*32 + 128)
   float* part_pb = part_co + static_cast<size_t>(296) * (kProj * kC + kProj);   // project_bwd: 16 * chunk rows x 386
   float* part_lb = part_pb + static_cast<size_t>(project_bwd_parts(FNO_BWD_CHUNK)) * project_bwd_row();   // lift_bwd
-  FNO_CUDA(cudaMemsetAsync(g->fc0_w, 0, sizeof(float) * kC * (5 + p), st), "memset");
-  FNO_CUDA(cudaMemsetAsync(g->fc0_b, 0, sizeof(float) * kC, st), "memset");
-  FNO_CUDA(cudaMemsetAsync(g->fc1_w, 0, sizeof(float) * kProj * kC, st), "memset");
-  FNO_CUDA(cudaMemsetAsync(g->fc1_b, 0, sizeof(float) * kProj, st), "memset");
-  FNO_CUDA(cudaMemsetAsync(g->fc2_w, 0, sizeof(float) * 2 * kProj, st), "memset");
-  FNO_CUDA(cudaMemsetAsync(g->fc2_b, 0, sizeof(float) * 2, st), "memset");
-  for (int l = 0; l < L; ++l) {
-    FNO_CUDA(cudaMemsetAsync(g->w0_w[l], 0, sizeof(float) * kC * kC, st), "memset");
-    FNO_CUDA(cudaMemsetAsync(g->w0_b[l], 0, sizeof(float) * kC, st), "memset");
-  }
+  // no memsets: every gradient is WRITTEN by its (first) reduction -- reduce_partials with accumulate = 0,
+  // lift_bwd_reduce, unpack_spectral_grads -- and only further batch chunks of the project stage accumulate
   // ---- project backward (batch chunks bound the dz1 scratch) -> d[0] = dpre_{L-1}
   const size_t act_elt = bf ? 2 : 4;
   for (int b0 = 0; b0 < batch; b0 += FNO_BWD_CHUNK) {
@@ -418,13 +410,14 @@ int fno_backward_ex(const fno_weights* w, const fno_weights_bwd* wb, const float
            : launch_project_bwd<float>(a_l, dp, mk, pre, w->fc1_w, w->fc1_b, w->fc2_w, dout, sc->dz1, part_pb, nb, st);
     FNO_CUDA(e, "project_bwd_kernel");
     const int rows = project_bwd_parts(nb), rs = project_bwd_row();
-    FNO_CUDA(launch_reduce_partials(part_pb, rows, rs, g->fc2_w, 2 * kProj, g->fc1_b, kProj, g->fc2_b, 2, st),
+    const int accum = b0 > 0 ? 1 : 0;
+    FNO_CUDA(launch_reduce_partials(part_pb, rows, rs, g->fc2_w, 2 * kProj, g->fc1_b, kProj, g->fc2_b, 2, accum, st),
              "reduce(fc2.weight | fc1.bias | fc2.bias)");
     int n_co = 0;
     e = bf ? launch_chan_outer<float, __nv_bfloat16, 128, 32>(sc->dz1, a_l, part_co, &n_co, nb, st)
            : launch_chan_outer<float, float, 128, 32>(sc->dz1, a_l, part_co, &n_co, nb, st);
     FNO_CUDA(e, "chan_outer_kernel(fc1)");
-    FNO_CUDA(launch_reduce_partials(part_co, n_co, kProj * kC + kProj, g->fc1_w, kProj * kC, nullptr, 0, nullptr, 0, st),
+    FNO_CUDA(launch_reduce_partials(part_co, n_co, kProj * kC + kProj, g->fc1_w, kProj * kC, nullptr, 0, nullptr, 0, accum, st),
              "reduce(fc1.weight)");
   }
   auto mark = [&](int seg) -> cudaError_t {   // the gradients of segment `seg` are final from here on (stream order)
@@ -442,7 +435,7 @@ int fno_backward_ex(const fno_weights* w, const fno_weights_bwd* wb, const float
     cudaError_t e = bf ? launch_chan_outer<float, __nv_bfloat16, 32, 32>(dpre, saved->act[l], part_co, &n_co, batch, st)
                        : launch_chan_outer<float, float, 32, 32>(dpre, saved->act[l], part_co, &n_co, batch, st);
     FNO_CUDA(e, "chan_outer_kernel(w0)");
-    FNO_CUDA(launch_reduce_partials(part_co, n_co, kC * kC + kC, g->w0_w[l], kC * kC, g->w0_b[l], kC, nullptr, 0, st),
+    FNO_CUDA(launch_reduce_partials(part_co, n_co, kC * kC + kC, g->w0_w[l], kC * kC, g->w0_b[l], kC, nullptr, 0, 0, st),
              "reduce(w0.weight | w0.bias)");
     FNO_TRY(fno_spectral_dft_fwd(dpre, sc->gm, batch, FNO_ACT_F32, inv, 2.f * inv, stream));
     FNO_CUDA(launch_spectral_wgrad(saved->xm[l], sc->gm, sc->gwk, batch, st), "spectral_wgrad_kernel");

@@ -44,6 +44,7 @@ constexpr int kPbOut = 3 * kProj + 2;   // per-CTA partial row: g_w2 (2 x 128) |
 struct ReduceSeg {
   float* out[3];
   int n[3];
+  int accumulate;   // 0: out = sum (no memset of the gradient needed), 1: out += sum (further batch chunks)
 };
 __global__ void __launch_bounds__(1024) reduce_partials_kernel(const float* __restrict__ partial, int n_parts, int row_stride,
                                                                ReduceSeg seg) {
@@ -66,18 +67,19 @@ __global__ void __launch_bounds__(1024) reduce_partials_kernel(const float* __re
     float t = red[0][tx];
 #pragma unroll
     for (int r = 1; r < 32; ++r) t += red[r][tx];
-    if (i < seg.n[0]) seg.out[0][i] += t;
-    else if (i < seg.n[0] + seg.n[1]) seg.out[1][i - seg.n[0]] += t;
-    else seg.out[2][i - seg.n[0] - seg.n[1]] += t;
+    float* dst = i < seg.n[0] ? seg.out[0] + i
+                 : (i < seg.n[0] + seg.n[1] ? seg.out[1] + (i - seg.n[0]) : seg.out[2] + (i - seg.n[0] - seg.n[1]));
+    *dst = seg.accumulate ? *dst + t : t;
   }
 }
 cudaError_t launch_reduce_partials(const float* partial, int n_parts, int row_stride, float* out0, int n0, float* out1, int n1,
-                                   float* out2, int n2, cudaStream_t stream) {
+                                   float* out2, int n2, int accumulate, cudaStream_t stream) {
   const int n_out = n0 + n1 + n2;
   if (n_parts <= 0 || n_out <= 0) return cudaSuccess;
   ReduceSeg seg;
   seg.out[0] = out0; seg.out[1] = out1; seg.out[2] = out2;
   seg.n[0] = n0; seg.n[1] = n1; seg.n[2] = n2;
+  seg.accumulate = accumulate;
   reduce_partials_kernel<<<(n_out + 31) / 32, 1024, 0, stream>>>(partial, n_parts, row_stride, seg);
   return cudaGetLastError();
 }
@@ -518,8 +520,8 @@ __global__ void lift_bwd_reduce_kernel(const float* __restrict__ partial, int n_
   const int c = i / (nin + 1), q = i % (nin + 1);
   float s = 0.f;
   for (int y = 0; y < n_parts; ++y) s += partial[(static_cast<size_t>(y) * kC + c) * (nin + 1) + q];
-  if (q < nin) g_w[c * nin + q] += s;
-  else g_b[c] += s;
+  if (q < nin) g_w[c * nin + q] = s;   // the only contribution: no memset of the gradient needed
+  else g_b[c] = s;
 }
 
 cudaError_t launch_lift_bwd(const float* da0, const float* inputs, const float* mask, const float* params,
