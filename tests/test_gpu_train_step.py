@@ -143,3 +143,31 @@ def test_gradients_and_training_are_bit_reproducible():
             assert torch.equal(finals[0][0][k], finals[1][0][k]), (act, "grad", k)
         for k in finals[0][1]:
             assert torch.equal(finals[0][1][k], finals[1][1][k]), (act, "param", k)
+
+
+def test_gradients_across_project_chunks_match_torch_port():
+    """70 samples = three chunks of the project backward (32 + 32 + 6): the first chunk's reduction WRITES the fc1 / fc2
+    gradients, the others accumulate (fno_backward: no memsets); every gradient against the CPU torch port of the
+    reference (same library calls, fp32) on the same batch."""
+    from cfdbench_b200 import Fno2d, loss_name_to_fn, synth
+    from oracle import fno_torch_port as port
+    p = 5
+    sd = synth.make_state_dict(61, n_params=p, spectral_gain=50.0)
+    batch = synth.make_batch(62, 70, "cavity")
+    m = Fno2d(in_chan=2, out_chan=2, n_case_params=p, loss_fn=loss_name_to_fn("nmse"), num_layers=4, hidden_dim=32,
+              modes1=12, modes2=12)
+    m.load_state_dict({k: torch.from_numpy(v) for k, v in sd.items()})
+    tb = {k: torch.from_numpy(v).cuda() for k, v in batch.items()}
+    for rep in range(2):   # the second pass runs into gradient buffers that hold the first pass's values
+        m.zero_grad()
+        out = m(**tb)
+        out["loss"]["nmse"].backward()
+    pp = port.params_from_numpy(sd, requires_grad=True)
+    cb = {k: torch.from_numpy(v) for k, v in batch.items()}
+    o = port.forward(pp, cb["inputs"], cb["case_params"], cb["mask"], label=cb["label"])
+    o["loss"]["nmse"].backward()
+    assert abs(out["loss"]["nmse"].item() - o["loss"]["nmse"].item()) < 1e-5 * abs(o["loss"]["nmse"].item())
+    for k, v in m.named_parameters():
+        ref = pp[k].grad.numpy()
+        err = np.linalg.norm(v.grad.cpu().numpy() - ref) / np.linalg.norm(ref)
+        assert err < 5e-5, (k, err)
