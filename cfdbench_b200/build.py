@@ -17,7 +17,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "libcfdbench_b200.so")
 STAMP = os.path.join(HERE, ".build_stamp")
-SOURCES = ["fno_abi.cu", "fno_dft_fwd.cu", "fno_dft_fwd_tc.cu", "fno_mode_mix.cu", "fno_block_tc.cu", "fno_block_fused.cu", "fno_pointwise.cu", "fno_project_tc.cu", "fno_project_ws.cu",
+SOURCES = ["fno_abi.cu", "fno_dft_fwd.cu", "fno_dft_fwd_tc.cu", "fno_mode_mix.cu", "fno_block_tc.cu", "fno_block_fused.cu", "fno_pointwise.cu", "fno_project_tc.cu", "fno_project_ws.cu", "fno_project_bwd_tc.cu",
            "fno_backward.cu", "fno_metrics.cu", "fno_train_step.cu"]
 NVCC_FLAGS = ["-std=c++17", "-O3", "-lineinfo", "-gencode", "arch=compute_100a,code=sm_100a",
               "-Xcompiler", "-fPIC"]
