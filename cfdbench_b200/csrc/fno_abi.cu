@@ -42,7 +42,8 @@ cudaError_t launch_project_bwd(const void*, const float*, const float*, const fl
 int project_bwd_parts(int);
 int project_bwd_row();
 cudaError_t launch_reduce_partials(const float*, int, int, float*, int, float*, int, float*, int, int, cudaStream_t);
-cudaError_t launch_project_bwd_tc(const float*, const float*, const float*, const float*, const float*, const float*, const float*,
+template <typename TAct>
+cudaError_t launch_project_bwd_tc(const void*, const float*, const float*, const float*, const float*, const float*, const float*,
                                   float*, float*, float*, int*, int, cudaStream_t);
 template <typename TP, typename TQ, int NJ, int NI>
 cudaError_t launch_chan_outer(const void*, const void*, float*, int*, int, cudaStream_t);
@@ -407,15 +408,14 @@ int fno_backward_ex(const fno_weights* w, const fno_weights_bwd* wb, const float
     float* dout = sc->d[0] + static_cast<size_t>(b0) * kC * kHW;
     const float* dp = dpreds + static_cast<size_t>(b0) * 2 * kHW;
     const float* mk = mask + static_cast<size_t>(b0) * kHW;
-    // fp32 storage: the tensor-core kernel (fno_project_bwd_tc.cu); FNO_PBWD_TC=0 selects the CUDA-core kernel, which is
-    // also the bf16-storage path
+    // the tensor-core kernel (fno_project_bwd_tc.cu); FNO_PBWD_TC=0 selects the CUDA-core kernel (A/B measurements)
     static const bool use_tc = [] { const char* v = getenv("FNO_PBWD_TC"); return !(v && v[0] == '0'); }();
     int rows = project_bwd_parts(nb);
     const int rs = project_bwd_row();
     cudaError_t e;
-    if (!bf && use_tc) {
-      e = launch_project_bwd_tc(reinterpret_cast<const float*>(a_l), dp, mk, pre, w->fc1_w, w->fc1_b, w->fc2_w, dout, sc->dz1,
-                                part_pb, &rows, nb, st);
+    if (use_tc) {
+      e = bf ? launch_project_bwd_tc<__nv_bfloat16>(a_l, dp, mk, pre, w->fc1_w, w->fc1_b, w->fc2_w, dout, sc->dz1, part_pb, &rows, nb, st)
+             : launch_project_bwd_tc<float>(a_l, dp, mk, pre, w->fc1_w, w->fc1_b, w->fc2_w, dout, sc->dz1, part_pb, &rows, nb, st);
     } else {
       e = bf ? launch_project_bwd<__nv_bfloat16>(a_l, dp, mk, pre, w->fc1_w, w->fc1_b, w->fc2_w, dout, sc->dz1, part_pb, nb, st)
              : launch_project_bwd<float>(a_l, dp, mk, pre, w->fc1_w, w->fc1_b, w->fc2_w, dout, sc->dz1, part_pb, nb, st);

@@ -1,9 +1,9 @@
 // Backward of the project stage (fc1 -> GELU -> fc2 -> mask; reference src/models/fno/fno2d.py:228-233 under autograd,
-// src/train_auto.py:255) on the tensor cores, fp32 activation storage.
+// src/train_auto.py:255) on the tensor cores, both activation storage types.
 //
 // Per tile of 128 pixels (thread = pixel x 32 hidden units, 16 warps = 4 TMEM lane quadrants x 4 column groups):
-//   1. x tile (fp32, [32 ch][128 px]) -> three bf16 pieces (24 significant bits) in the MN-major 128B-swizzled operand layout
-//      TMA would have produced for bf16 storage; the loads of the NEXT tile are issued before this tile's arithmetic.
+//   1. x tile ([32 ch][128 px]) -> three bf16 pieces (24 significant bits; bf16 storage: the plane itself, one piece) in the
+//      MN-major 128B-swizzled operand layout; the loads of the NEXT tile are issued before this tile's arithmetic.
 //   2. GEMM1  z[128 px][128] = X W1^T           kind::f16, 6 piece products x 2 K steps, accumulator in tensor memory
 //   3. epilogue A: z + b1 -> GELU and GELU' sharing one erfc;  dz = (w2[0] d0 + w2[1] d1) GELU'(z)  (d = dpreds * mask);
 //      dz goes to global memory (the fc1 weight gradient is chan_outer's job) AND back into tensor memory as tf32 hi / lo;
@@ -13,7 +13,7 @@
 //   5. epilogue B: da (x GELU'(pre) of the last Fourier block) -> d_out.
 // The phases of a tile run one after the other (one CTA per SM, __syncthreads between phases): even so the tile costs
 // ~8k cycles against ~35k for the CUDA-core kernel it replaces (project_bwd_kernel: both GEMMs as register-operand
-// FFMA2, fma-pipe bound at half rate), which remains the path for bf16 activation storage.
+// FFMA2, fma-pipe bound at half rate; kept behind FNO_PBWD_TC=0).
 // Deterministic: per-CTA partial row [g_w2 256 | g_b1 128 | g_b2 2], reduced by reduce_partials in CTA order.
 #include "fno_common.cuh"
 #include "tc_common.cuh"
@@ -86,8 +86,9 @@ __device__ __forceinline__ void qb_gelu_both(float x, float& g, float& dg) {
   dg = fmaf(x, pdf, cdf);
 }
 
+template <typename TAct>
 __global__ void __launch_bounds__(kQbThreads, 1)
-    project_bwd_tc_kernel(const float* __restrict__ a,        // [B][32][4096]  a_L (fp32 storage)
+    project_bwd_tc_kernel(const TAct* __restrict__ a,         // [B][32][4096]  a_L
                           const float* __restrict__ dpreds,   // [B][2][4096]
                           const float* __restrict__ mask,     // [B][4096]
                           const float* __restrict__ pre,      // [B][32][4096] pre-activation of the last block (or null)
@@ -141,19 +142,24 @@ __global__ void __launch_bounds__(kQbThreads, 1)
   // x piece conversion: thread = (channel c, group of 8 pixels)
   const int xc = tid >> 4, xg = tid & 15;
   const uint32_t x_dst = (xg >> 3) * 4096 + xc * 128 + (((xg & 7) ^ (xc & 7)) << 4);
-  auto x_src = [&](int tile) {
+  constexpr bool kBf = sizeof(TAct) == 2;   // bf16 storage: the plane IS the first piece, the other two are zero
+  auto x_load = [&](int tile, float4& va, float4& vb) {   // 8 consecutive pixels of channel xc (fp32: 32 B, bf16: 16 B in va)
     const int b = tile / kQbTilesPerSample, px0 = (tile % kQbTilesPerSample) * kQbM;
-    return reinterpret_cast<const float4*>(a + (static_cast<size_t>(b) * kC + xc) * kHW + px0 + xg * 8);
+    const TAct* src = a + (static_cast<size_t>(b) * kC + xc) * kHW + px0 + xg * 8;
+    va = __ldg(reinterpret_cast<const float4*>(src));
+    if constexpr (!kBf) vb = __ldg(reinterpret_cast<const float4*>(src) + 1);
   };
   float4 xa = make_float4(0.f, 0.f, 0.f, 0.f), xb = xa;
-  if (first < n_tiles) { const float4* s = x_src(first); xa = __ldg(s); xb = __ldg(s + 1); }
+  if (first < n_tiles) x_load(first, xa, xb);
   float acc_b2[2] = {0.f, 0.f};   // sum over this thread's pixels of d0, d1 (warps with cg == 0 only)
 
   int it = 0;
   for (int tile = first; tile < n_tiles; tile += stride, ++it) {
     const int b = tile / kQbTilesPerSample, pix = (tile % kQbTilesPerSample) * kQbM + q * 32 + lane;
     // ---- phase 1: x pieces of this tile -> shared memory (the registers were loaded one tile ago)
-    {
+    if constexpr (kBf) {
+      *reinterpret_cast<float4*>(sm.xp[0] + x_dst) = xa;
+    } else {
       const float xv[8] = {xa.x, xa.y, xa.z, xa.w, xb.x, xb.y, xb.z, xb.w};
       uint32_t pk[3][4];
 #pragma unroll
@@ -176,9 +182,11 @@ __global__ void __launch_bounds__(kQbThreads, 1)
     // ---- phase 2: GEMM1 (one elected thread), everybody else fetches the next tile's x and this tile's per-pixel inputs
     if (warp == 0 && tc::elect_one()) {
       constexpr uint32_t idesc = fz_idesc_bf16(kQbM, kProj) | kAMajorMN;
-      constexpr int pa[6] = {0, 0, 1, 0, 1, 2}, pb[6] = {0, 1, 0, 2, 1, 0};   // x piece, W piece: all products down to 2^-24
+      // x piece, W piece: all products down to 2^-24 (bf16 storage: x has one piece)
+      constexpr int pa[6] = {0, 0, 0, 1, 1, 2}, pb[6] = {0, 1, 2, 0, 1, 0};
+      constexpr int n_prod = kBf ? 3 : 6;
 #pragma unroll
-      for (int t = 0; t < 6; ++t) {
+      for (int t = 0; t < n_prod; ++t) {
         const uint32_t x_s = tc::smem_addr(sm.xp[pa[t]]), w_s = tc::smem_addr(sm.w1p[pb[t]]);
 #pragma unroll
         for (int ks = 0; ks < 2; ++ks)
@@ -188,7 +196,7 @@ __global__ void __launch_bounds__(kQbThreads, 1)
       tc::mma_commit(&sm.bar_g1);
     }
     __syncwarp();
-    if (tile + stride < n_tiles) { const float4* s = x_src(tile + stride); xa = __ldg(s); xb = __ldg(s + 1); }
+    if (tile + stride < n_tiles) x_load(tile + stride, xa, xb);
     const float mk = __ldg(mask + static_cast<size_t>(b) * kHW + pix);
     const float d0 = __ldg(dpreds + (static_cast<size_t>(b) * 2 + 0) * kHW + pix) * mk;
     const float d1 = __ldg(dpreds + (static_cast<size_t>(b) * 2 + 1) * kHW + pix) * mk;
@@ -312,10 +320,11 @@ __global__ void __launch_bounds__(kQbThreads, 1)
 }
 
 // returns the number of partial rows written through *n_parts
-cudaError_t launch_project_bwd_tc(const float* a, const float* dpreds, const float* mask, const float* pre, const float* w1,
+template <typename TAct>
+cudaError_t launch_project_bwd_tc(const void* a, const float* dpreds, const float* mask, const float* pre, const float* w1,
                                   const float* b1, const float* w2, float* d_out, float* dz1, float* partial, int* n_parts,
                                   int batch, cudaStream_t stream) {
-  auto kern = project_bwd_tc_kernel;
+  auto kern = project_bwd_tc_kernel<TAct>;
   constexpr size_t smem = sizeof(QbSmem);
   static PerDeviceLaunch pd;
   int n_sm = 0;
@@ -323,9 +332,14 @@ cudaError_t launch_project_bwd_tc(const float* a, const float* dpreds, const flo
   if (e0 != cudaSuccess) return e0;
   const int n_tiles = batch * kQbTilesPerSample;
   const int grid = n_tiles < n_sm ? n_tiles : n_sm;
-  kern<<<grid, kQbThreads, smem, stream>>>(a, dpreds, mask, pre, w1, b1, w2, d_out, dz1, partial, n_tiles);
+  kern<<<grid, kQbThreads, smem, stream>>>(static_cast<const TAct*>(a), dpreds, mask, pre, w1, b1, w2, d_out, dz1, partial, n_tiles);
   *n_parts = grid;
   return cudaGetLastError();
 }
+template cudaError_t launch_project_bwd_tc<float>(const void*, const float*, const float*, const float*, const float*, const float*,
+                                                  const float*, float*, float*, float*, int*, int, cudaStream_t);
+template cudaError_t launch_project_bwd_tc<__nv_bfloat16>(const void*, const float*, const float*, const float*, const float*,
+                                                          const float*, const float*, float*, float*, float*, int*, int,
+                                                          cudaStream_t);
 
 }  // namespace fno
