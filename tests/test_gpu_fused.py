@@ -313,6 +313,26 @@ def test_bf16_full_batch_samples_and_properties():
     assert_within_flip_ambiguity(y1[idx].cpu().numpy(), sd, sub, "B=256 samples")
 
 
+@pytest.mark.parametrize("act", ["bfloat16", "float32"])
+def test_batch_invariance_ragged_large_batch(act):
+    """A sample's prediction must not depend on the batch it travels in: 333 samples (every persistent kernel recycles its
+    rings several times; ragged 128-sample mode tiles; an incomplete last round of block units, not split) against the same
+    samples run as batches of 5 and of 1 -- bitwise, every kernel being free of cross-sample reductions."""
+    p = 5
+    sd = synth.make_state_dict(41, n_params=p, spectral_gain=100.0)
+    m = make_model(sd, p, act_dtype=act)
+    batch = synth.make_batch(42, 333, "cavity", with_label=False)
+    inp, cp, mk = (torch.from_numpy(batch[k]).cuda() for k in ("inputs", "case_params", "mask"))
+    with torch.no_grad():
+        big = m.generate(inp, cp, mk)
+        idx = torch.tensor([0, 127, 128, 255, 332], device="cuda")
+        small = m.generate(inp[idx], cp[idx], mk[idx])
+        one = m.generate(inp[332:333], cp[332:333], mk[332:333])
+    assert torch.isfinite(big).all()
+    assert torch.equal(big[idx], small)
+    assert torch.equal(big[332:333], one)
+
+
 def test_bf16_gradients_and_train_step_vs_port_with_rounding():
     """Training in bf16 storage (saved activations bf16, project_bwd / chan_outer bf16 templates): gradients against the
     torch port that rounds the same tensors (straight-through rounding, as the kernels do)."""
