@@ -399,11 +399,11 @@ __global__ void __launch_bounds__(kFzThreads, 1)
         }
 #pragma unroll 1
         for (int st = 0; st < 6; ++st) {
-          // pacing: the stages of unit k >= 1 go behind super-tiles 2..5 of unit k-1 -- after the converters have released
+          // pacing: the stages of unit k >= 1 go behind super-tiles 1..6 of unit k-1 -- after the converters have released
           // D1 (d1_free, around super-tile 1) and before they want the new D1 (three super-tiles ahead of the MMAs).  This
           // thread observes EVERY phase of the pace barriers, in order, so the one-bit parity stays unambiguous.
           if (k >= 1) {
-            const int s_hi = (k - 1) * kFzSPU + 2 + (2 * st) / 3;   // super-tiles 2,2,3,4,4,5 of the previous unit
+            const int s_hi = (k - 1) * kFzSPU + 1 + st;   // one stage behind each of super-tiles 1..6 (A/B on one box: 2..5 0.4 % slower)
             for (; pace_next <= s_hi && pace_next < n_super_all; ++pace_next)
               mbar_wait(&sm.pace[fz_bar(pace_next)], fz_phase(pace_next));
           }
