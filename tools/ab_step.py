@@ -1,3 +1,6 @@
+"""Same-box A/B of the rollout step: `python tools/ab_step.py default|<tag>` times 7 x 20 graph-replayed steps (B=256, bf16)
+with libcfdbench_b200.so or with a variant built into cfdbench_b200/build/<tag>/lib.so (nvcc -D... of the same sources).
+Alternate the tags inside ONE gpurun call: box-to-box spread (power cap) is ~4 %, same-box repeatability ~0.3 %."""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from cfdbench_b200 import _lib
