@@ -91,6 +91,9 @@ struct FzSmem {
   // super-tiles, and with an odd ring size a role would otherwise see only every other phase of a slot's barrier, which
   // the one-bit phase parity cannot express (a wait could match the completion of three super-tiles earlier).
   alignas(8) uint64_t ready[2 * kFzR], slot_free[2 * kFzR], d2_full[2 * kFzR];
+  // x_free[s]: the 1x1-convolution MMAs of the super-tile have completed: its x tiles may be refilled while its C2R MMAs
+  // still run (the TMA round trip of the slot's next user starts ~1,000 cycles earlier)
+  uint64_t x_free[2 * kFzR];
   // pace[s]: the same completion event once more, consumed by the GEMM1 thread: it spreads the 54 MMAs of the NEXT unit's
   // inverse-kx GEMM over the super-tiles of the current unit (one stage per super-tile) instead of queueing them in one
   // ~3,200-cycle burst in front of the tile MMAs the three-slot ring is waiting for
@@ -159,6 +162,7 @@ __global__ void __launch_bounds__(kFzThreads, 1)
     for (int i = 0; i < 2 * kFzR; ++i) {
       mbar_init(&sm.ready[i], kFzReadyCount);
       mbar_init(&sm.slot_free[i], 1);
+      mbar_init(&sm.x_free[i], 1);
       mbar_init(&sm.d2_full[i], 1);
       mbar_init(&sm.pace[i], 1);
     }
@@ -349,7 +353,7 @@ __global__ void __launch_bounds__(kFzThreads, 1)
         tc::fence_after_thread_sync();
         FZ_T(2, S, 2);
 #pragma unroll
-        for (int i = 0; i < kFzTS; ++i) {
+        for (int i = 0; i < kFzTS; ++i) {   // 1x1 convolution: per tile (the x tiles differ)
           const uint32_t d = tmem + kFzColD2 + (ss * kFzTS + i) * 32;
           const uint32_t x_s = tc::smem_addr(sm.x[ss][i]);
 #pragma unroll
@@ -359,7 +363,16 @@ __global__ void __launch_bounds__(kFzThreads, 1)
               if (!FZ_KNOCK(1) || (pc | ks) == 0)
               fz_mma_f16_ss(d, fz_desc_sw128(x_s + ks * 2048, 4096, 1024),
                             tc::make_smem_desc(w_s + pc * 2048 + ks * 1024, 512, 128), idesc_c, (pc | ks) ? 1u : 0u);
-          const uint32_t z_hi = tc::smem_addr(sm.bt[ss][i]), z_lo = z_hi + 6144;
+        }
+        tc::mma_commit(&sm.x_free[fz_bar(S)]);
+        {
+          // C2R stage: the constant E is the same for every tile, so BOTH tiles of the super-slot go through one N = 64
+          // instruction per K step -- their Zt operands are two 128-byte column blocks kFzBtBytes apart (the descriptor's
+          // MN-direction stride), their accumulators two adjacent 32-column blocks: 18 MMAs instead of 36.
+          static_assert(kFzTS == 2, "the C2R MMAs cover exactly two tiles");
+          constexpr uint32_t idesc_e2 = tc::make_idesc_tf32(128, 64) | kBMajorMN;
+          const uint32_t d = tmem + kFzColD2 + (ss * kFzTS) * 32;
+          const uint32_t z_hi = tc::smem_addr(sm.bt[ss][0]), z_lo = z_hi + 6144;
 #pragma unroll
           for (int pass = 0; pass < 3; ++pass) {
             const uint32_t a_t = tmem + kFzColE + ((pass == 1) ? 48u : 0u);
@@ -367,7 +380,7 @@ __global__ void __launch_bounds__(kFzThreads, 1)
 #pragma unroll
             for (int ks = 0; ks < 6; ++ks)
               if (!FZ_KNOCK(2))
-              fz_mma_tf32_ts(d, a_t + ks * 8, fz_desc_sw128_32(b_s + ks * 1024, 0, 512), idesc_e, 1u);
+              fz_mma_tf32_ts(d, a_t + ks * 8, fz_desc_sw128_32(b_s + ks * 1024, kFzBtBytes, 512), idesc_e2, 1u);
           }
         }
         tc::mma_commit(&sm.slot_free[fz_bar(S)]);
@@ -443,7 +456,7 @@ __global__ void __launch_bounds__(kFzThreads, 1)
         const int ss = S % kFzR;
         const int u = super_unit(S), t0 = super_local(S) * kFzTS;
         const int b = u >> 1;
-        if (S >= kFzR) mbar_wait(&sm.slot_free[fz_bar(S - kFzR)], fz_phase(S - kFzR));
+        if (S >= kFzR) mbar_wait(&sm.x_free[fz_bar(S - kFzR)], fz_phase(S - kFzR));
         uint64_t* rdy = &sm.ready[fz_bar(S)];
         mbar_expect_tx(rdy, kFzTS * kFzXBytes);
 #pragma unroll
