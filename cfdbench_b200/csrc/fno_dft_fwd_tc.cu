@@ -154,21 +154,26 @@ __global__ void __launch_bounds__(kTdThreads, 1)
     bulk_g2s(sm.ta, ta_tab, kTdTABytes, &sm.ta_bar);
   }
   if (warp == kTdMmaAWarp) tc::tmem_alloc<kTdTmemCols>(&sm.tmem_base);
+  // the A2 values of this thread are requested before the barrier: their L2 round trip overlaps the TMEM allocation
+  const bool loads_a2 = warp < kTdConvWarps && (warp & 3) < 3;
+  float a2v[32];
+  if (loads_a2) {
+    const int m = (warp & 3) * 32 + lane, cbase = (warp >> 2) * 32;
+#pragma unroll
+    for (int j = 0; j < 32; ++j) a2v[j] = __ldg(a2_tab + (cbase + j) * kTdA2Rows + m);
+  }
   tc::fence_before_thread_sync();
   __syncthreads();
   tc::fence_after_thread_sync();
   const uint32_t tmem = sm.tmem_base;
-  if (warp < kTdConvWarps && (warp & 3) < 3) {
+  if (loads_a2) {
     // constant A2 operand -> tensor memory (lanes 96..127 of the M = 128 operand are never written: their products land
     // in accumulator rows nobody reads).  The table is stored column-major in LANE order, so that a warp reads 128
     // contiguous bytes per column; 4 warps per lane quadrant, 32 columns each.
-    const int m = (warp & 3) * 32 + lane, cbase = (warp >> 2) * 32;
-    float v[32];
-#pragma unroll
-    for (int j = 0; j < 32; ++j) v[j] = __ldg(a2_tab + (cbase + j) * kTdA2Rows + m);   // one L2 round trip, not two
+    const int cbase = (warp >> 2) * 32;
 #pragma unroll
     for (int c0 = 0; c0 < 32; c0 += 16)
-      tc::tmem_st16(tmem + kTdColA2 + cbase + c0 + (static_cast<uint32_t>((warp & 3) * 32) << 16), v + c0);
+      tc::tmem_st16(tmem + kTdColA2 + cbase + c0 + (static_cast<uint32_t>((warp & 3) * 32) << 16), a2v + c0);
     tc::tmem_wait_st();
   }
   tc::fence_before_thread_sync();
