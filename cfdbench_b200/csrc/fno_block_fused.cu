@@ -221,9 +221,8 @@ __global__ void __launch_bounds__(kFzThreads, 1)
       tc::tmem_st16(tmem + kFzColE + cbase + c0 + (static_cast<uint32_t>((warp & 3) * 32) << 16), e_val + c0);
     tc::tmem_wait_st();
   }
-  mbar_wait(&sm.f_bar, 0);
   tc::fence_before_thread_sync();
-  __syncthreads();
+  __syncthreads();   // (the twiddle operand's bulk copy is awaited by its only reader, the GEMM1 thread)
   tc::fence_after_thread_sync();
 #ifdef FNO_FZ_TRACE
   if (fz_tr != nullptr && threadIdx.x == 0) fz_tr[4 * 256 * 8 + blockIdx.x * 4 + 1] = clock64();
@@ -397,6 +396,7 @@ __global__ void __launch_bounds__(kFzThreads, 1)
     if (tc::elect_one()) {
       const uint32_t f_hi = tc::smem_addr(sm.f), f_lo = f_hi + kFzFBytes / 2;
       int pace_next = 0;   // first super-tile whose completion this thread has not consumed yet
+      mbar_wait(&sm.f_bar, 0);   // twiddle operand (prologue bulk copy)
       constexpr uint32_t idesc_g64 = tc::make_idesc_tf32(128, 64) | kAMajorMN;
       constexpr uint32_t idesc_g32 = tc::make_idesc_tf32(128, 32) | kAMajorMN;
 #pragma unroll 1

@@ -111,9 +111,15 @@ __global__ void __launch_bounds__(kQbThreads, 1)
     fence_mbar_init();
   }
   if (warp == 0) tc::tmem_alloc<512>(&sm.tmem_base);
-  for (int e = tid; e < kProj * kC; e += kQbThreads) {   // w1[j][i]
+  constexpr int kW1PerThread = kProj * kC / kQbThreads;   // 8: all loads first (one L2 round trip), then the conversions
+  float w1v[kW1PerThread];
+#pragma unroll
+  for (int it = 0; it < kW1PerThread; ++it) w1v[it] = __ldg(w1 + tid + it * kQbThreads);
+#pragma unroll
+  for (int it = 0; it < kW1PerThread; ++it) {   // w1[j][i]
+    const int e = tid + it * kQbThreads;
     const int j = e / kC, i = e % kC;
-    const float wv = w1[e];
+    const float wv = w1v[it];
     __nv_bfloat16 p0, p1, p2;
     qb_split3(wv, p0, p1, p2);
     const uint32_t off = qb_kmajor16(j, i, kProj);

@@ -75,10 +75,21 @@ __global__ void __launch_bounds__(kPwThreads, 1)
     fence_mbar_init();
   }
   if (warp == kPwMmaWarp) tc::tmem_alloc<512>(&sm.tmem_base);
-  for (int e = tid; e < kProj * kC; e += kPwThreads) {   // w1[j][i] -> B[n = j][k = i]
+  // all loads of a thread first (one L2 round trip instead of eight dependent ones), then the conversions
+  constexpr int kW1PerThread = (kProj * kC + kPwThreads - 1) / kPwThreads;
+  float w1v[kW1PerThread];
+#pragma unroll
+  for (int it = 0; it < kW1PerThread; ++it) {
+    const int e = tid + it * kPwThreads;
+    w1v[it] = e < kProj * kC ? __ldg(w1 + e) : 0.f;
+  }
+#pragma unroll
+  for (int it = 0; it < kW1PerThread; ++it) {   // w1[j][i] -> B[n = j][k = i]
+    const int e = tid + it * kPwThreads;
+    if (e >= kProj * kC) break;
     const int j = e / kC, i = e % kC;
     __nv_bfloat16 p0, p1, p2;
-    pw_split3(w1[e], p0, p1, p2);
+    pw_split3(w1v[it], p0, p1, p2);
     const uint32_t off = pw_kmajor16(j, i, kProj);
     *reinterpret_cast<__nv_bfloat16*>(sm.w1[0] + off) = p0;
     *reinterpret_cast<__nv_bfloat16*>(sm.w1[1] + off) = p1;
