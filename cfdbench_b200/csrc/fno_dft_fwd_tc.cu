@@ -11,23 +11,25 @@
 //      blocks of ONE N = 80 operand (72 used), so a plane pair costs 4 MMAs and the terms are added when the
 //      accumulator is read.
 //  stage B (along h):  F[(kxi,part)][(q,p)] = sum_{(ri,h)} A2[(kxi,part)][(ri,h)] * G_p[h][q][ri],  kxi = 0..23
-//      tcgen05.mma kind::tf32 as 3xTF32, M = 128 (48 used), N = 48 (12 q x 4 planes), K = 128.  A2 = (c, s | -s, c) is a
-//      constant that lives in TENSOR MEMORY (hi and lo, 256 columns) for the whole kernel, so a stage-B MMA reads only
-//      its 1.5 KB B operand from shared memory.  The B operand is stage A's accumulator, read from TMEM by the thread
-//      that owns row (p,h), split into tf32 hi/lo and scattered K-major (4-byte stores, conflict-free through a skewed
-//      K stride).  Because x is real, G[h][-q] = conj(G[h][q]): only q >= 0 is computed and stage B produces all 24
-//      kept kx rows (kx = 0..11 and 52..63) of the 12 kept columns directly.
-//  epilogue: rows (kxi,re) / (kxi,im) sit in adjacent TMEM lanes; lane pairs exchange halves with two shuffles per
-//      column and write 16 bytes each (32 contiguous bytes per mode and 4-plane batch).
+//      tcgen05.mma kind::tf32 as 3xTF32, N = 48 (12 q x 4 planes), K = 128.  A2 = (c, s | -s, c) is a constant that lives
+//      in TENSOR MEMORY for the whole kernel with its tf32 hi and lo parts STACKED IN M (lanes 0-15 / 16-31 of three lane
+//      quadrants hold 16 rows of A2_hi / the same rows of A2_lo): two passes over the B operand (G_hi, G_lo) of 16 MMAs each
+//      give all four hi/lo products, and a stage-B MMA reads only its 1.5 KB B operand from shared memory.  The B operand
+//      is stage A's accumulator, read from TMEM by the thread that owns row (p,h), split into tf32 hi (truncated) / lo
+//      (exact residual, rounded) and scattered K-major (4-byte stores, conflict-free through a skewed K stride).  Because
+//      x is real, G[h][-q] = conj(G[h][q]): only q >= 0 is computed and stage B produces all 24 kept kx rows
+//      (kx = 0..11 and 52..63) of the 12 kept columns directly.
+//  epilogue: drains the accumulator into registers at once (single D_B buffer, released immediately), adds the hi / lo
+//      row blocks (lane ^ 16), pairs the (kxi,re) / (kxi,im) lanes (lane ^ 1) and writes 16 bytes per lane and column.
 //
-// Warp-specialised, one persistent 768-thread CTA per SM, every hand-off an mbarrier (round 1's version of this kernel
+// Warp-specialised, one persistent 832-thread CTA per SM, every hand-off an mbarrier (round 1's version of this kernel
 // ran the same two GEMMs from 16 worker warps that fetched, split and stored in turn: 43 us, latency-serial):
-//   warp 22 lane 0   producer: one 32 KB TMA per batch into a 3-slot ring
-//   warp 18          issues stage A (8 MMAs per batch) as soon as a batch has landed and D_A has been drained
-//   warps 0..15      converters: D_A -> registers (36 columns each) -> sum of terms -> tf32 hi/lo -> B2 (double buffered)
-//   warp 19          issues stage B (48 MMAs per batch) into one of two accumulators
-//   warps 16,17 / 20,21   two epilogue groups (lane quadrants 0 and 1 hold the 48 result rows), alternate batches
-// Tensor time per batch ~ 4 x 45 + 48 x 24 cycles; 13.8 batches per SM at B = 256.
+//   warp 25 lane 0        producer: one 32 KB TMA per batch into a 3-slot ring (released when stage A has completed)
+//   warp 19               issues stage A (8 MMAs per batch) into one of two D_A buffers
+//   warps 0..15           converters: D_A -> registers (36 columns each) -> sum of terms -> tf32 hi/lo -> B2 (double buffered)
+//   warps 23, 24          issue stage B (32 MMAs per batch) for even / odd batches
+//   warps 16-18 / 20-22   two epilogue groups (lane quadrants 0..2 hold the 96 stacked result rows), alternate batches
+// Tensor time per batch ~ 8 x 55 + 32 x 26 cycles; 13.8 batches per SM at B = 256; 25 us per launch.
 // The register-FFT kernel (fno_dft_fwd.cu) remains for fp32 storage and the fp32 gradients of the backward pass.
 #include "fno_common.cuh"
 #include "tc_common.cuh"
