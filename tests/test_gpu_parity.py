@@ -147,9 +147,10 @@ def test_mode_mix_and_pack_kernels(lib):
 
 @pytest.mark.parametrize("batch", [1, 3, 41])
 def test_dft_fwd_tensor_core_kernel_bf16_storage(lib, batch):
-    """bf16 planes through dft_fwd_tc_kernel (two chained UMMA GEMMs) and through the register-FFT kernel the forward
-    path uses; 41 samples = 328 plane batches, i.e. up to three per persistent CTA (pipeline steady state + ragged
-    tail).  The inputs are bf16-exact, so the comparison with the float64 oracle measures the arithmetic only."""
+    """bf16 planes through dft_fwd_tc_kernel (two chained UMMA GEMMs; the forward path of bf16 storage) by its own entry
+    point and through fno_spectral_dft_fwd (which routes bf16 planes to it unless FNO_DFT_TC=0 selects the register-FFT
+    kernel); 41 samples = 328 plane batches, i.e. up to three per persistent CTA (pipeline steady state + ragged tail).
+    The inputs are bf16-exact, so the comparison with the float64 oracle measures the arithmetic only."""
     from cfdbench_b200 import _lib
     rng = np.random.default_rng(10 + batch)
     x = torch.from_numpy(rng.standard_normal((batch, 32, 64, 64)).astype(np.float32)).to(torch.bfloat16)
