@@ -321,3 +321,13 @@ def test_bench_reference_arm_prints_one_contract_line():
     assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
     import bench
     assert d["config"]["workload"] == bench.workload_name(2)
+
+
+def test_bench_train_line_names_the_allreduce_mode():
+    """bench.py: the train-step line states the all-reduce mode actually used (Fno2d.dp_segments), only when world > 1."""
+    import bench
+    one = bench._train_result(2.0, 64, 1, "cavity", True, "f32", "one")
+    assert one["value"] == 500.0 and one["global_batch"] == 64 and "all-reduce" not in one["what"]
+    two = bench._train_result(2.0, 64, 2, "cylinder", True, "bf16", "one")
+    assert two["global_batch"] == 128 and "ONE NCCL AVG all-reduce" in two["what"] and "bf16 storage" in two["what"]
+    assert "per gradient segment" in bench._train_result(2.0, 64, 2, "cavity", False, "f32", "all")["what"]
